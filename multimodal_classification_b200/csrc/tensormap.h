@@ -1,0 +1,15 @@
+// Host-side TMA descriptor factory.  cuTensorMapEncodeTiled is resolved through
+// cudaGetDriverEntryPoint so the library has no link-time dependency on libcuda.so (it must load —
+// though not compute — on a CPU-only box for the ABI tests).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace vb {
+// bf16, row-major [outer, inner] with `ld` elements between rows, 128-byte swizzle, OOB reads give zeros.
+int make_tensor_map_2d(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld,
+                       int box_inner, int box_outer);
+// bf16, [d2, d1, d0] with element strides (s2, s1, 1); 128-byte swizzle.
+int make_tensor_map_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1,
+                       int64_t s2, int box0, int box1, int box2);
+}  // namespace vb
