@@ -76,6 +76,121 @@ typedef struct vb_gemm_args {
 
 int vb_gemm_bf16(const vb_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Row-wise bandwidth kernels (one warp per row, 16-byte accesses, fp32 math on bf16 storage).
+ * Dropout masks are a pure function of (*seed, site, element index): forward and backward regenerate
+ * them, nothing is stored.  `seed` is a DEVICE pointer so that a captured CUDA graph sees a new seed on
+ * every replay.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum vb_dtype { VB_DT_F32 = 0, VB_DT_I32 = 1, VB_DT_I64 = 2 } vb_dtype;
+
+/* y = LayerNorm(dropout_in(x) + res) * gamma + beta, then dropout_out  — BertLayerNorm (eps inside the sqrt, biased
+ * variance) fused with the dropout and residual add that precede it:
+ *   models/vilbert_facebook_arch.py:63-76 (BertLayerNorm), :156-160 (BertSelfOutput), :197-201 (BertOutput),
+ *   :329-336 (BiOutput), :100-104 (VisualEmbeddings: x = image term, res = location term, dropout_out).
+ * Backward: dx = grad wrt x (masked), dres = grad wrt res, dgamma/dbeta/dbias (= column sum of dx, the bias gradient of
+ * the dense layer that produced x) are ATOMICALLY ACCUMULATED into fp32 — zero them first. */
+typedef struct vb_layernorm_args {
+  const void* x;        /* bf16 [m,h] */
+  const void* res;      /* bf16 [m,h] or NULL */
+  const float* gamma;   /* fp32 [h] */
+  const float* beta;    /* fp32 [h] */
+  void* y;              /* bf16 [m,h]            (forward) */
+  float* mean;          /* fp32 [m]  written by forward, read by backward */
+  float* rstd;          /* fp32 [m] */
+  const void* dy;       /* bf16 [m,h]            (backward) */
+  void* dx;             /* bf16 [m,h] or NULL */
+  void* dres;           /* bf16 [m,h] or NULL */
+  float* dgamma;        /* fp32 [h] or NULL */
+  float* dbeta;         /* fp32 [h] or NULL */
+  float* dbias;         /* fp32 [h] or NULL */
+  int64_t ldx, ldres, ldy, lddy, lddx, lddres; /* elements */
+  int32_t m, h;         /* h in {256,512,768,1024,2048} */
+  float eps;
+  float p_in, p_out;    /* dropout probabilities (0 = off) */
+  uint32_t site_in, site_out;
+  const uint64_t* seed; /* device pointer, may be NULL when both p are 0 */
+} vb_layernorm_args;
+int vb_layernorm_fwd(const vb_layernorm_args* args, void* stream);
+int vb_layernorm_bwd(const vb_layernorm_args* args, void* stream);
+
+/* Text embeddings: y = dropout(LayerNorm(word[ids] + type[type_ids] + pos[0..t)))  — transformers BertEmbeddings.forward,
+ * called at models/vilbert_facebook_arch.py:524.  Tables are the fp32 master parameters.  Backward scatter-adds into the
+ * fp32 table gradients (atomics; word row 0 = padding_idx receives nothing). */
+typedef struct vb_embed_args {
+  const int32_t* ids;       /* [b*t] */
+  const int32_t* type_ids;  /* [b*t] or NULL (all zero) */
+  const float* word;        /* [vocab,h] */
+  const float* pos;         /* [>=t,h] */
+  const float* type;        /* [2,h] */
+  const float* gamma;
+  const float* beta;
+  void* y;                  /* bf16 [b*t,h] */
+  float* mean;
+  float* rstd;
+  const void* dy;           /* bf16 [b*t,h]  (backward) */
+  float* dword; float* dpos; float* dtype; float* dgamma; float* dbeta;  /* each may be NULL (frozen) */
+  int32_t b, t, h, vocab;
+  float eps, p_out;
+  uint32_t site_out;
+  const uint64_t* seed;
+} vb_embed_args;
+int vb_embed_text_fwd(const vb_embed_args* args, void* stream);
+int vb_embed_text_bwd(const vb_embed_args* args, void* stream);
+
+/* out[n] += sum_m x[m,n]  (bias gradients; autograd of nn.Linear bias) */
+int vb_colsum_bf16(const void* x, int64_t ld, int32_t m, int32_t n, float* out, void* stream);
+/* fp32 -> bf16 (inputs; weight shadows).  The multi form converts many parameter tensors in one launch: `segs` is a
+ * device array of {const float* src; bf16* dst; int64 n}, block i converts 8192 elements of segs[block_seg[i]] starting
+ * at block_off[i]. */
+int vb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+int vb_cast_f32_bf16_multi(const void* segs, const int32_t* block_seg, const int64_t* block_off, int32_t num_blocks,
+                           void* stream);
+/* out = (1.0f - (float)mask) * -10000.0f, bit-exact with models/vilbert_facebook_arch.py:530-540 */
+int vb_mask_bias(const void* mask, int32_t mask_dtype, float* out, int32_t n, void* stream);
+/* int64 ids / labels -> int32 with a range check ([lo,hi); *err_flag = 1 on violation, like the index error torch raises) */
+int vb_i64_to_i32(const int64_t* src, int32_t* dst, int32_t n, int32_t lo, int32_t hi, int32_t* err_flag, void* stream);
+/* y = dropout(x) element-wise (classifier nn.Dropout(0.1), models/vilbert_facebook_arch.py:573,576) */
+int vb_dropout_bf16(const void* x, void* y, int64_t n, float p, uint32_t site, const uint64_t* seed, void* stream);
+/* dx = dy * act'(y) for tanh (BertPooler :407) and ReLU (classifier :575), through the activation output y */
+int vb_act_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, int32_t act, void* stream);
+/* image_location_embeddings (Linear(5,1024), models/vilbert_facebook_arch.py:92-94,102): forward term and its gradients */
+int vb_loc_embed_fwd(const float* loc, const float* w, const float* b, void* out, int32_t m, int32_t n, int32_t kdim,
+                     void* stream);
+int vb_loc_embed_bwd(const void* ds, const float* loc, float* dw, float* db, int32_t m, int32_t n, int32_t kdim,
+                     void* stream);
+/* classifier tail Linear(1024,num_labels) + CrossEntropyLoss(mean), models/vilbert_facebook_arch.py:577, 637-639.
+ * fwd: logits fp32 [b,c], probs = softmax(logits), *loss (labels may be NULL -> loss 0).
+ * bwd: dlogits = *dloss * (probs - onehot)/b + dlogits_ext;  dw[c,k], db[c] (overwritten), dh bf16 [b,k]. */
+int vb_cls_ce_fwd(const void* h, const float* w, const float* bias, const int32_t* labels, float* logits, float* probs,
+                  float* loss, int32_t bsz, int32_t kdim, int32_t c, void* stream);
+int vb_cls_ce_bwd(const void* h, const float* w, const int32_t* labels, const float* probs, const float* dloss,
+                  const float* dlogits_ext, float* dw, float* db, void* dh, int32_t bsz, int32_t kdim, int32_t c,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused softmax attention on tcgen05/TMEM: one CTA per (sample, head), sq, sk <= 128, d in {64,128}.
+ *   out = dropout(softmax(q k^T * scale + mask_bias[b, key])) v
+ * Serves BertSelfAttention (models/vilbert_facebook_arch.py:126-144) and both directions of BiAttention (:253-294):
+ * q, k, v are independent strided views (pointer to the first head's column, row stride in elements, sq / sk rows
+ * per sample).  lse [batch, heads, 128] fp32 is written by forward and read by backward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vb_attn_args {
+  const void* q; const void* k; const void* v;   /* bf16 */
+  int64_t ldq, ldk, ldv;
+  void* out; int64_t ldo;                        /* bf16 [batch*sq, heads*d] view */
+  float* lse;
+  const float* mask_bias;                        /* fp32 [batch, sk] or NULL */
+  int32_t batch, heads, sq, sk, d;
+  float scale;
+  float p_drop; uint32_t site; const uint64_t* seed;
+  const void* dout; int64_t lddo;                /* backward */
+  void* dq; void* dk; void* dv;
+  int64_t lddq, lddk, lddv;
+} vb_attn_args;
+int vb_attention_fwd(const vb_attn_args* args, void* stream);
+int vb_attention_bwd(const vb_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

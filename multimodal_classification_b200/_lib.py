@@ -31,6 +31,43 @@ class GemmArgs(C.Structure):
     ]
 
 
+class LayerNormArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("res", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p), ("dy", C.c_void_p), ("dx", C.c_void_p), ("dres", C.c_void_p),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
+        ("ldx", C.c_int64), ("ldres", C.c_int64), ("ldy", C.c_int64), ("lddy", C.c_int64), ("lddx", C.c_int64),
+        ("lddres", C.c_int64),
+        ("m", C.c_int32), ("h", C.c_int32), ("eps", C.c_float), ("p_in", C.c_float), ("p_out", C.c_float),
+        ("site_in", C.c_uint32), ("site_out", C.c_uint32), ("seed", C.c_void_p),
+    ]
+
+
+class EmbedArgs(C.Structure):
+    _fields_ = [
+        ("ids", C.c_void_p), ("type_ids", C.c_void_p), ("word", C.c_void_p), ("pos", C.c_void_p), ("type", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("y", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("dy", C.c_void_p), ("dword", C.c_void_p), ("dpos", C.c_void_p), ("dtype", C.c_void_p), ("dgamma", C.c_void_p),
+        ("dbeta", C.c_void_p),
+        ("b", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("vocab", C.c_int32), ("eps", C.c_float),
+        ("p_out", C.c_float), ("site_out", C.c_uint32), ("seed", C.c_void_p),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64), ("lse", C.c_void_p), ("mask_bias", C.c_void_p),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32), ("d", C.c_int32),
+        ("scale", C.c_float), ("p_drop", C.c_float), ("site", C.c_uint32), ("seed", C.c_void_p),
+        ("dout", C.c_void_p), ("lddo", C.c_int64), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("lddq", C.c_int64), ("lddk", C.c_int64), ("lddv", C.c_int64),
+    ]
+
+
+DT_F32, DT_I32, DT_I64 = 0, 1, 2
+
 _lib = None
 
 
@@ -53,6 +90,27 @@ def _declare(l: C.CDLL) -> None:
     l.vb_build_info.restype = C.c_char_p
     l.vb_gemm_bf16.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
     l.vb_gemm_bf16.restype = C.c_int
+    vp, i32, i64, f32, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32
+    sigs = {
+        "vb_layernorm_fwd": [C.POINTER(LayerNormArgs), vp], "vb_layernorm_bwd": [C.POINTER(LayerNormArgs), vp],
+        "vb_embed_text_fwd": [C.POINTER(EmbedArgs), vp], "vb_embed_text_bwd": [C.POINTER(EmbedArgs), vp],
+        "vb_attention_fwd": [C.POINTER(AttnArgs), vp], "vb_attention_bwd": [C.POINTER(AttnArgs), vp],
+        "vb_colsum_bf16": [vp, i64, i32, i32, vp, vp],
+        "vb_cast_f32_bf16": [vp, vp, i64, vp],
+        "vb_cast_f32_bf16_multi": [vp, vp, vp, i32, vp],
+        "vb_mask_bias": [vp, i32, vp, i32, vp],
+        "vb_i64_to_i32": [vp, vp, i32, i32, i32, vp, vp],
+        "vb_dropout_bf16": [vp, vp, i64, f32, u32, vp, vp],
+        "vb_act_bwd_bf16": [vp, vp, vp, i64, i32, vp],
+        "vb_loc_embed_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
+        "vb_loc_embed_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],
+        "vb_cls_ce_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "vb_cls_ce_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
 
 
 def check(rc: int, what: str) -> None:

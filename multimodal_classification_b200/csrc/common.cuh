@@ -8,18 +8,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace vb {
+#include "../../include/vilbert_b200.h"  // vb_status codes returned across the C ABI
 
-// ----------------------------------------------------------------------------------------------
-// error codes returned across the C ABI (see include/vilbert_b200.h)
-// ----------------------------------------------------------------------------------------------
-enum : int {
-  VB_OK = 0,
-  VB_ERR_BAD_ARG = -1,
-  VB_ERR_CUDA = -2,
-  VB_ERR_UNSUPPORTED = -3,
-  VB_ERR_NO_DRIVER = -4,
-};
+namespace vb {
 
 #ifndef VB_SPIN_LIMIT
 // every mbarrier wait is bounded: a broken pipeline traps instead of hanging the GPU box.
@@ -272,7 +263,7 @@ __host__ __device__ inline uint32_t dropout_threshold(float p) {
     cudaError_t _e = (expr);                                 \
     if (_e != cudaSuccess) {                                 \
       vb_set_last_error(#expr, cudaGetErrorString(_e));      \
-      return vb::VB_ERR_CUDA;                                \
+      return VB_ERR_CUDA;                                \
     }                                                        \
   } while (0)
 
@@ -280,7 +271,7 @@ __host__ __device__ inline uint32_t dropout_threshold(float p) {
   do {                                        \
     if (!(cond)) {                            \
       vb_set_last_error(#cond, msg);          \
-      return vb::VB_ERR_BAD_ARG;              \
+      return VB_ERR_BAD_ARG;              \
     }                                         \
   } while (0)
 

@@ -69,3 +69,238 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     args.block_n, args.splits, args.max_ctas = block_n, splits, max_ctas
     _lib.check(_lib.lib().vb_gemm_bf16(C.byref(args), _stream()), "vb_gemm_bf16")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ row-wise kernels
+def _ld(t):
+    return 0 if t is None else t.stride(0)
+
+
+def _ln_args(x, res, gamma, beta, mean, rstd, eps, p_in, site_in, p_out, site_out, seed):
+    _need_cuda(x, res, gamma, beta, mean, rstd, seed)
+    m, h = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1
+    a = _lib.LayerNormArgs()
+    a.x, a.res, a.gamma, a.beta = x.data_ptr(), _ptr(res), gamma.data_ptr(), _ptr(beta)
+    a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+    a.ldx, a.ldres = x.stride(0), _ld(res)
+    a.m, a.h, a.eps = m, h, eps
+    a.p_in, a.p_out, a.site_in, a.site_out = p_in, p_out, site_in, site_out
+    a.seed = _ptr(seed)
+    return a
+
+
+def layernorm_fwd(x, res, gamma, beta, y, mean, rstd, *, eps=1e-12, p_in=0.0, site_in=0, p_out=0.0, site_out=0,
+                  seed=None):
+    """y = dropout_out(LN(dropout_in(x) + res)); BertLayerNorm + the dropout / residual before it
+    (reference models/vilbert_facebook_arch.py:63-76, 156-160, 197-201, 329-336)."""
+    a = _ln_args(x, res, gamma, beta, mean, rstd, eps, p_in, site_in, p_out, site_out, seed)
+    _need_cuda(y)
+    a.y, a.ldy = y.data_ptr(), y.stride(0)
+    _lib.check(_lib.lib().vb_layernorm_fwd(C.byref(a), _stream()), "vb_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, res, gamma, mean, rstd, *, dx=None, dres=None, dgamma=None, dbeta=None, dbias=None,
+                  eps=1e-12, p_in=0.0, site_in=0, p_out=0.0, site_out=0, seed=None):
+    """Gradients of layernorm_fwd; dgamma / dbeta / dbias are accumulated atomically (zero them first)."""
+    a = _ln_args(x, res, gamma, None, mean, rstd, eps, p_in, site_in, p_out, site_out, seed)
+    _need_cuda(dy, dx, dres, dgamma, dbeta, dbias)
+    a.dy, a.lddy = dy.data_ptr(), dy.stride(0)
+    a.dx, a.lddx, a.dres, a.lddres = _ptr(dx), _ld(dx), _ptr(dres), _ld(dres)
+    a.dgamma, a.dbeta, a.dbias = _ptr(dgamma), _ptr(dbeta), _ptr(dbias)
+    _lib.check(_lib.lib().vb_layernorm_bwd(C.byref(a), _stream()), "vb_layernorm_bwd")
+
+
+def _emb_args(ids, type_ids, word, pos, typ, gamma, beta, mean, rstd, b, t, eps, p_out, site_out, seed):
+    _need_cuda(ids, type_ids, word, pos, typ, gamma, beta, mean, rstd, seed)
+    assert ids.dtype == torch.int32 and (type_ids is None or type_ids.dtype == torch.int32)
+    assert word.dtype == torch.float32 and word.is_contiguous() and pos.is_contiguous() and typ.is_contiguous()
+    a = _lib.EmbedArgs()
+    a.ids, a.type_ids, a.word, a.pos, a.type = ids.data_ptr(), _ptr(type_ids), word.data_ptr(), pos.data_ptr(), typ.data_ptr()
+    a.gamma, a.beta, a.mean, a.rstd = gamma.data_ptr(), _ptr(beta), mean.data_ptr(), rstd.data_ptr()
+    a.b, a.t, a.h, a.vocab = b, t, word.shape[1], word.shape[0]
+    a.eps, a.p_out, a.site_out, a.seed = eps, p_out, site_out, _ptr(seed)
+    assert pos.shape[0] >= t
+    return a
+
+
+def embed_text_fwd(ids, type_ids, word, pos, typ, gamma, beta, y, mean, rstd, b, t, *, eps=1e-12, p_out=0.0,
+                   site_out=0, seed=None):
+    """transformers BertEmbeddings.forward as called at models/vilbert_facebook_arch.py:524."""
+    a = _emb_args(ids, type_ids, word, pos, typ, gamma, beta, mean, rstd, b, t, eps, p_out, site_out, seed)
+    a.y = y.data_ptr()
+    _lib.check(_lib.lib().vb_embed_text_fwd(C.byref(a), _stream()), "vb_embed_text_fwd")
+    return y
+
+
+def embed_text_bwd(dy, ids, type_ids, word, pos, typ, gamma, mean, rstd, b, t, *, dword=None, dpos=None, dtype=None,
+                   dgamma=None, dbeta=None, eps=1e-12, p_out=0.0, site_out=0, seed=None):
+    a = _emb_args(ids, type_ids, word, pos, typ, gamma, None, mean, rstd, b, t, eps, p_out, site_out, seed)
+    _need_cuda(dy, dword, dpos, dtype, dgamma, dbeta)
+    a.dy = dy.data_ptr()
+    a.dword, a.dpos, a.dtype, a.dgamma, a.dbeta = _ptr(dword), _ptr(dpos), _ptr(dtype), _ptr(dgamma), _ptr(dbeta)
+    _lib.check(_lib.lib().vb_embed_text_bwd(C.byref(a), _stream()), "vb_embed_text_bwd")
+
+
+def colsum(x, out):
+    """out[n] += sum_m x[m, n] (bias gradient)."""
+    _need_cuda(x, out)
+    assert x.dtype == torch.bfloat16 and out.dtype == torch.float32 and x.stride(1) == 1
+    _lib.check(_lib.lib().vb_colsum_bf16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), _stream()),
+               "vb_colsum_bf16")
+    return out
+
+
+def cast_bf16(src, dst):
+    _need_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.is_contiguous() and dst.is_contiguous()
+    assert src.numel() == dst.numel()
+    _lib.check(_lib.lib().vb_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "vb_cast_f32_bf16")
+    return dst
+
+
+class MultiCast:
+    """One launch that refreshes every bf16 weight shadow from its fp32 master (pointer table on the device)."""
+    CHUNK = 256 * 8 * 4
+
+    def __init__(self, pairs, device):
+        import numpy as np
+        segs = np.zeros((len(pairs), 3), dtype=np.int64)
+        block_seg, block_off = [], []
+        self._keep = pairs
+        for i, (src, dst) in enumerate(pairs):
+            assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.is_contiguous() and dst.is_contiguous()
+            assert src.numel() == dst.numel() and src.is_cuda and dst.is_cuda
+            assert src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0
+            segs[i] = (src.data_ptr(), dst.data_ptr(), src.numel())
+            for off in range(0, src.numel(), self.CHUNK):
+                block_seg.append(i)
+                block_off.append(off)
+        self.src_ptrs = [s.data_ptr() for s, _ in pairs]
+        self.segs = torch.from_numpy(segs).to(device)
+        self.block_seg = torch.tensor(block_seg, dtype=torch.int32, device=device)
+        self.block_off = torch.tensor(block_off, dtype=torch.int64, device=device)
+
+    def valid(self):
+        return all(s.data_ptr() == p for (s, _), p in zip(self._keep, self.src_ptrs))
+
+    def run(self):
+        _lib.check(_lib.lib().vb_cast_f32_bf16_multi(self.segs.data_ptr(), self.block_seg.data_ptr(),
+                                                     self.block_off.data_ptr(), self.block_seg.numel(), _stream()),
+                   "vb_cast_f32_bf16_multi")
+
+
+_MASK_DT = {torch.float32: _lib.DT_F32, torch.int32: _lib.DT_I32, torch.int64: _lib.DT_I64}
+
+
+def mask_bias(mask, out):
+    """(1.0 - mask) * -10000.0, reference models/vilbert_facebook_arch.py:530-540."""
+    _need_cuda(mask, out)
+    if mask.dtype not in _MASK_DT:
+        raise _lib.VbError(f"attention mask dtype {mask.dtype} is not supported (int64, int32, float32)")
+    assert mask.is_contiguous() and out.dtype == torch.float32 and out.numel() == mask.numel()
+    _lib.check(_lib.lib().vb_mask_bias(mask.data_ptr(), _MASK_DT[mask.dtype], out.data_ptr(), mask.numel(), _stream()),
+               "vb_mask_bias")
+    return out
+
+
+def i64_to_i32(src, dst, lo, hi, err_flag=None):
+    _need_cuda(src, dst, err_flag)
+    assert src.dtype == torch.int64 and dst.dtype == torch.int32 and src.is_contiguous()
+    _lib.check(_lib.lib().vb_i64_to_i32(src.data_ptr(), dst.data_ptr(), src.numel(), lo, hi, _ptr(err_flag), _stream()),
+               "vb_i64_to_i32")
+    return dst
+
+
+def dropout(x, y, p, site, seed):
+    _need_cuda(x, y, seed)
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.bfloat16
+    _lib.check(_lib.lib().vb_dropout_bf16(x.data_ptr(), y.data_ptr(), x.numel(), p, site, seed.data_ptr(), _stream()),
+               "vb_dropout_bf16")
+    return y
+
+
+def act_bwd(dy, y, dx, act):
+    _need_cuda(dy, y, dx)
+    assert dy.is_contiguous() and y.is_contiguous() and dx.is_contiguous()
+    _lib.check(_lib.lib().vb_act_bwd_bf16(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), dy.numel(), act, _stream()),
+               "vb_act_bwd_bf16")
+    return dx
+
+
+def loc_embed_fwd(loc, w, b, out):
+    _need_cuda(loc, w, b, out)
+    assert loc.dtype == torch.float32 and loc.is_contiguous() and w.is_contiguous() and out.is_contiguous()
+    m, k = loc.shape
+    _lib.check(_lib.lib().vb_loc_embed_fwd(loc.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), m, w.shape[0], k,
+                                           _stream()), "vb_loc_embed_fwd")
+    return out
+
+
+def loc_embed_bwd(ds, loc, dw, db):
+    _need_cuda(ds, loc, dw, db)
+    assert ds.is_contiguous() and loc.is_contiguous()
+    m, k = loc.shape
+    _lib.check(_lib.lib().vb_loc_embed_bwd(ds.data_ptr(), loc.data_ptr(), dw.data_ptr(), _ptr(db), m, ds.shape[1], k,
+                                           _stream()), "vb_loc_embed_bwd")
+
+
+def cls_ce_fwd(h, w, bias, labels, logits, probs, loss):
+    _need_cuda(h, w, bias, labels, logits, probs, loss)
+    assert h.is_contiguous() and w.is_contiguous() and h.dtype == torch.bfloat16 and w.dtype == torch.float32
+    _lib.check(_lib.lib().vb_cls_ce_fwd(h.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(labels), logits.data_ptr(),
+                                        probs.data_ptr(), _ptr(loss), h.shape[0], h.shape[1], w.shape[0], _stream()),
+               "vb_cls_ce_fwd")
+
+
+def cls_ce_bwd(h, w, labels, probs, dloss, dlogits_ext, dw, db, dh):
+    _need_cuda(h, w, labels, probs, dloss, dlogits_ext, dw, db, dh)
+    _lib.check(_lib.lib().vb_cls_ce_bwd(h.data_ptr(), w.data_ptr(), _ptr(labels), probs.data_ptr(), _ptr(dloss),
+                                        _ptr(dlogits_ext), _ptr(dw), _ptr(db), dh.data_ptr(), h.shape[0], h.shape[1],
+                                        w.shape[0], _stream()), "vb_cls_ce_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_args(q, k, v, lse, mask_bias_t, batch, heads, sq, sk, d, scale, p_drop, site, seed):
+    _need_cuda(q, k, v, lse, mask_bias_t, seed)
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.stride(-1) == 1 and t.dim() == 2
+    assert q.shape[0] == batch * sq and k.shape[0] == batch * sk and v.shape[0] == batch * sk
+    assert q.shape[1] == heads * d and k.shape[1] == heads * d and v.shape[1] == heads * d
+    assert lse.dtype == torch.float32 and lse.numel() == batch * heads * 128
+    a = _lib.AttnArgs()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.ldq, a.ldk, a.ldv = q.stride(0), k.stride(0), v.stride(0)
+    a.lse, a.mask_bias = lse.data_ptr(), _ptr(mask_bias_t)
+    if mask_bias_t is not None:
+        assert mask_bias_t.dtype == torch.float32 and mask_bias_t.numel() == batch * sk and mask_bias_t.is_contiguous()
+    a.batch, a.heads, a.sq, a.sk, a.d = batch, heads, sq, sk, d
+    a.scale, a.p_drop, a.site, a.seed = scale, p_drop, site, _ptr(seed)
+    return a
+
+
+def attention_fwd(q, k, v, out, lse, *, batch, heads, sq, sk, d, mask_bias=None, scale=None, p_drop=0.0, site=0,
+                  seed=None):
+    """out = dropout(softmax(q k^T * scale + mask_bias)) v per (sample, head); q/k/v/out are 2-D strided views
+    [batch*seq, heads*d] (reference models/vilbert_facebook_arch.py:126-144 and :253-294)."""
+    scale = (1.0 / d ** 0.5) if scale is None else scale
+    a = _attn_args(q, k, v, lse, mask_bias, batch, heads, sq, sk, d, scale, p_drop, site, seed)
+    _need_cuda(out)
+    assert out.shape == q.shape and out.stride(1) == 1
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    _lib.check(_lib.lib().vb_attention_fwd(C.byref(a), _stream()), "vb_attention_fwd")
+    return out
+
+
+def attention_bwd(dout, q, k, v, lse, dq, dk, dv, *, batch, heads, sq, sk, d, mask_bias=None, scale=None, p_drop=0.0,
+                  site=0, seed=None):
+    scale = (1.0 / d ** 0.5) if scale is None else scale
+    a = _attn_args(q, k, v, lse, mask_bias, batch, heads, sq, sk, d, scale, p_drop, site, seed)
+    _need_cuda(dout, dq, dk, dv)
+    for t in (dout, dq, dk, dv):
+        assert t.dtype == torch.bfloat16 and t.stride(1) == 1
+    a.dout, a.lddo = dout.data_ptr(), dout.stride(0)
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    _lib.check(_lib.lib().vb_attention_bwd(C.byref(a), _stream()), "vb_attention_bwd")
