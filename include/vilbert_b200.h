@@ -152,6 +152,8 @@ int vb_mask_bias(const void* mask, int32_t mask_dtype, float* out, int32_t n, vo
 int vb_i64_to_i32(const int64_t* src, int32_t* dst, int32_t n, int32_t lo, int32_t hi, int32_t* err_flag, void* stream);
 /* y = dropout(x) element-wise (classifier nn.Dropout(0.1), models/vilbert_facebook_arch.py:573,576) */
 int vb_dropout_bf16(const void* x, void* y, int64_t n, float p, uint32_t site, const uint64_t* seed, void* stream);
+/* *seed = lcg(*seed): one tiny launch at the head of every training forward (dropout mask stream) */
+int vb_seed_advance(uint64_t* seed, void* stream);
 /* dx = dy * act'(y) for tanh (BertPooler :407) and ReLU (classifier :575), through the activation output y */
 int vb_act_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, int32_t act, void* stream);
 /* image_location_embeddings (Linear(5,1024), models/vilbert_facebook_arch.py:92-94,102): forward term and its gradients */

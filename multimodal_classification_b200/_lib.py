@@ -101,6 +101,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_mask_bias": [vp, i32, vp, i32, vp],
         "vb_i64_to_i32": [vp, vp, i32, i32, i32, vp, vp],
         "vb_dropout_bf16": [vp, vp, i64, f32, u32, vp, vp],
+        "vb_seed_advance": [vp, vp],
         "vb_act_bwd_bf16": [vp, vp, vp, i64, i32, vp],
         "vb_loc_embed_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
         "vb_loc_embed_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],

@@ -787,3 +787,14 @@ extern "C" int vb_cls_ce_bwd(const void* h, const float* w, const int32_t* label
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;
 }
+
+// dropout seed stream: advanced once per training forward INSIDE the captured graph, so every replay draws new masks
+__global__ void seed_advance_kernel(unsigned long long* seed) {
+  *seed = *seed * 6364136223846793005ull + 1442695040888963407ull;
+}
+extern "C" int vb_seed_advance(uint64_t* seed, void* stream) {
+  VB_REQUIRE(seed != nullptr, "null seed");
+  seed_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)seed);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}

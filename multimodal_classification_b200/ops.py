@@ -221,6 +221,11 @@ def dropout(x, y, p, site, seed):
     return y
 
 
+def seed_advance(seed):
+    _need_cuda(seed)
+    _lib.check(_lib.lib().vb_seed_advance(seed.data_ptr(), _stream()), "vb_seed_advance")
+
+
 def act_bwd(dy, y, dx, act):
     _need_cuda(dy, y, dx)
     assert dy.is_contiguous() and y.is_contiguous() and dx.is_contiguous()

@@ -1,0 +1,878 @@
+"""B200-native ``ViLBERTForClassification``: the drop-in for the reference's
+``models/vilbert_facebook_arch.py`` (class at :554, forward at :610-641).
+
+The module tree exists only to hold fp32 master ``nn.Parameter``s under the reference's names (Appendix A of SURVEY.md:
+523 tensors, identical ``state_dict`` layout).  ``forward`` never calls a torch compute op: it stages the batch into
+static device buffers and replays a hand-scheduled sequence of kernels from ``libvilbert_b200.so`` (engine below) —
+forward and, through one ``torch.autograd.Function``, backward — captured in CUDA graphs, with the text and visual
+streams of the encoder running concurrently between co-attention joins.
+
+Precision: fp32 master weights and gradients, bf16 weight shadows / activations, fp32 accumulation everywhere.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import VbError
+
+CO_ATTENTION_TEXT_LAYERS = (1, 3, 5, 7, 9, 11)  # reference :457
+
+
+def get_facebook_vilbert_config() -> Dict[str, Any]:
+    """Same dictionary as the reference's ``get_facebook_vilbert_config`` (vilbert_facebook_arch.py:35-60)."""
+    return {
+        "hidden_size": 768, "num_attention_heads": 12, "num_hidden_layers": 12, "intermediate_size": 3072,
+        "hidden_dropout_prob": 0.1, "attention_probs_dropout_prob": 0.1, "max_position_embeddings": 512,
+        "vocab_size": 30522,
+        "v_hidden_size": 1024, "v_num_attention_heads": 8, "v_num_hidden_layers": 6, "v_intermediate_size": 1024,
+        "v_hidden_dropout_prob": 0.1, "v_attention_probs_dropout_prob": 0.1,
+        "num_co_attention_layers": 6, "bi_hidden_size": 1024,
+        "v_feature_size": 2048, "v_loc_size": 5,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parameter containers (names = the reference's state_dict keys)
+# ---------------------------------------------------------------------------------------------------------------------
+class _LayerNormParams(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(n))
+        self.bias = nn.Parameter(torch.zeros(n))
+
+
+class _Holder(nn.Module):
+    pass
+
+
+def _self_attention(h):
+    m = _Holder()
+    m.query, m.key, m.value = nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, h)
+    return m
+
+
+def _dense_ln(i, o):
+    m = _Holder()
+    m.dense = nn.Linear(i, o)
+    m.LayerNorm = _LayerNormParams(o)
+    return m
+
+
+def _dense(i, o):
+    m = _Holder()
+    m.dense = nn.Linear(i, o)
+    return m
+
+
+def _bert_layer(h, inter):
+    m = _Holder()
+    m.attention = _Holder()
+    m.attention.self = _self_attention(h)
+    m.attention.output = _dense_ln(h, h)
+    m.intermediate = _dense(h, inter)
+    m.output = _dense_ln(inter, h)
+    return m
+
+
+def _co_layer(cfg):
+    H, Hv, bi = cfg["hidden_size"], cfg["v_hidden_size"], cfg["bi_hidden_size"]
+    m = _Holder()
+    b = m.biattention = _Holder()
+    b.query1, b.key1, b.value1 = nn.Linear(Hv, bi), nn.Linear(Hv, bi), nn.Linear(Hv, bi)
+    b.query2, b.key2, b.value2 = nn.Linear(H, bi), nn.Linear(H, bi), nn.Linear(H, bi)
+    o = m.biOutput = _Holder()
+    o.dense1, o.LayerNorm1 = nn.Linear(bi, Hv), _LayerNormParams(Hv)
+    o.dense2, o.LayerNorm2 = nn.Linear(bi, H), _LayerNormParams(H)
+    o.q_dense1, o.q_dense2 = nn.Linear(bi, Hv), nn.Linear(bi, H)  # present, never used (reference :319-320)
+    m.v_intermediate = _dense(Hv, cfg["v_intermediate_size"])
+    m.v_output = _dense_ln(cfg["v_intermediate_size"], Hv)
+    m.t_intermediate = _dense(H, cfg["intermediate_size"])
+    m.t_output = _dense_ln(cfg["intermediate_size"], H)
+    return m
+
+
+class _TextEmbeddings(nn.Module):
+    """Parameter layout of transformers ``BertEmbeddings`` (the reference reuses ``BertModel(...).embeddings``)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        H = cfg["hidden_size"]
+        self.word_embeddings = nn.Embedding(cfg["vocab_size"], H, padding_idx=0)
+        self.position_embeddings = nn.Embedding(cfg["max_position_embeddings"], H)
+        self.token_type_embeddings = nn.Embedding(2, H)
+        self.LayerNorm = nn.LayerNorm(H, eps=1e-12)
+        for e in (self.word_embeddings, self.position_embeddings, self.token_type_embeddings):
+            nn.init.normal_(e.weight, mean=0.0, std=0.02)
+        with torch.no_grad():
+            self.word_embeddings.weight[0].zero_()
+
+
+class _Backbone(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        H, Hv = cfg["hidden_size"], cfg["v_hidden_size"]
+        self.embeddings = _TextEmbeddings(cfg)
+        ve = self.v_embeddings = _Holder()
+        ve.image_embeddings = nn.Linear(cfg["v_feature_size"], Hv)
+        ve.image_location_embeddings = nn.Linear(cfg["v_loc_size"], Hv)
+        ve.LayerNorm = _LayerNormParams(Hv)
+        enc = self.encoder = _Holder()
+        enc.layer = nn.ModuleList([_bert_layer(H, cfg["intermediate_size"]) for _ in range(cfg["num_hidden_layers"])])
+        enc.v_layer = nn.ModuleList([_bert_layer(Hv, cfg["v_intermediate_size"]) for _ in range(cfg["v_num_hidden_layers"])])
+        enc.c_layer = nn.ModuleList([_co_layer(cfg) for _ in range(cfg["num_co_attention_layers"])])
+        self.t_pooler = _dense(H, cfg["bi_hidden_size"])
+        self.v_pooler = _dense(Hv, Hv)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# flat parameter storage
+# ---------------------------------------------------------------------------------------------------------------------
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class _FlatParams:
+    """All parameters live in ONE fp32 device buffer (and gradients in a second one with the same layout) so that
+    fused operands (q|k|v weights and biases) are contiguous without copies, the bf16 shadow refresh and the gradient
+    zeroing are single launches, and the data-parallel all-reduce works on contiguous byte ranges.
+
+    Layout: [W: GEMM weight matrices, shadowed in bf16][S: biases / LayerNorm / location weights / embedding tables
+    (gradients accumulated with atomics -> zeroed every backward)][U: parameters the forward never reads]."""
+
+    def __init__(self, model: "ViLBERTForClassification", device):
+        cfg = model.config
+        named = dict(model.named_parameters())
+        order_w: List[str] = []
+        order_s: List[str] = []
+
+        def lin(prefix, fused=None):
+            order_w.append(prefix + ".weight")
+            order_s.append(prefix + ".bias")
+
+        def ln(prefix):
+            order_s.extend([prefix + ".weight", prefix + ".bias"])
+
+        def bert_layer(p):
+            for n in ("query", "key", "value"):
+                order_w.append(f"{p}.attention.self.{n}.weight")
+            for n in ("query", "key", "value"):
+                order_s.append(f"{p}.attention.self.{n}.bias")
+            lin(p + ".attention.output.dense"); ln(p + ".attention.output.LayerNorm")
+            lin(p + ".intermediate.dense"); lin(p + ".output.dense"); ln(p + ".output.LayerNorm")
+
+        for i in range(cfg["num_hidden_layers"]):
+            bert_layer(f"bert.encoder.layer.{i}")
+        for i in range(cfg["v_num_hidden_layers"]):
+            bert_layer(f"bert.encoder.v_layer.{i}")
+        for i in range(cfg["num_co_attention_layers"]):
+            p = f"bert.encoder.c_layer.{i}"
+            for side in ("1", "2"):
+                for n in ("query", "key", "value"):
+                    order_w.append(f"{p}.biattention.{n}{side}.weight")
+                for n in ("query", "key", "value"):
+                    order_s.append(f"{p}.biattention.{n}{side}.bias")
+            lin(p + ".biOutput.dense1"); ln(p + ".biOutput.LayerNorm1")
+            lin(p + ".biOutput.dense2"); ln(p + ".biOutput.LayerNorm2")
+            lin(p + ".v_intermediate.dense"); lin(p + ".v_output.dense"); ln(p + ".v_output.LayerNorm")
+            lin(p + ".t_intermediate.dense"); lin(p + ".t_output.dense"); ln(p + ".t_output.LayerNorm")
+        lin("bert.v_embeddings.image_embeddings")
+        lin("bert.t_pooler.dense"); lin("bert.v_pooler.dense"); lin("classifier.1")
+        order_s += ["bert.v_embeddings.image_location_embeddings.weight", "bert.v_embeddings.image_location_embeddings.bias",
+                    "bert.v_embeddings.LayerNorm.weight", "bert.v_embeddings.LayerNorm.bias",
+                    "classifier.4.weight", "classifier.4.bias",
+                    "bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.bias",
+                    "bert.embeddings.token_type_embeddings.weight", "bert.embeddings.position_embeddings.weight",
+                    "bert.embeddings.word_embeddings.weight"]
+        used = set(order_w) | set(order_s)
+        order_u = [k for k in named if k not in used]
+        assert all("q_dense" in k for k in order_u), order_u
+
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for k in order_w:
+            n = named[k].numel()
+            assert n % 64 == 0, k
+            self.offsets[k] = off
+            off += n
+        self.w_end = off
+        for k in order_s:
+            self.offsets[k] = off
+            off += _align(named[k].numel())
+        self.s_end = off
+        for k in order_u:
+            self.offsets[k] = off
+            off += _align(named[k].numel())
+        self.total = off
+        self.used = used
+        self.device = device
+        self.master = torch.empty(self.total, dtype=torch.float32, device=device)
+        self.master.zero_()
+        self.grad = torch.zeros(self.s_end, dtype=torch.float32, device=device)
+        self.shadow = torch.empty(self.w_end, dtype=torch.bfloat16, device=device)
+        self.named = named
+        for k, p in named.items():
+            o, n = self.offsets[k], p.numel()
+            view = self.master[o:o + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+        self._ptrs = {k: p.data_ptr() for k, p in named.items()}
+        self._version = -1
+
+    # fused q|k|v biases are laid out back to back: check rather than assume
+    def check_contiguous(self, keys: List[str]):
+        o = self.offsets[keys[0]]
+        for k in keys:
+            assert self.offsets[k] == o, (k, self.offsets[k], o)
+            o += self.named[k].numel()
+
+    def intact(self) -> bool:
+        return all(p.data_ptr() == self._ptrs[k] for k, p in self.named.items())
+
+    def versions(self) -> int:
+        return sum(p._version for p in self.named.values())
+
+    def w(self, key: str, rows: Optional[int] = None) -> torch.Tensor:
+        """bf16 shadow of a GEMM weight (optionally `rows` rows starting at this key: fused q|k|v)."""
+        p = self.named[key]
+        r = p.shape[0] if rows is None else rows
+        o = self.offsets[key]
+        return self.shadow[o:o + r * p.shape[1]].view(r, p.shape[1])
+
+    def m(self, key: str, numel: Optional[int] = None) -> torch.Tensor:
+        """fp32 master view (1-D, optionally spanning fused neighbours)."""
+        n = self.named[key].numel() if numel is None else numel
+        o = self.offsets[key]
+        return self.master[o:o + n]
+
+    def g(self, key: str, shape=None, numel: Optional[int] = None) -> torch.Tensor:
+        """fp32 gradient view."""
+        p = self.named[key]
+        n = p.numel() if numel is None else numel
+        o = self.offsets[key]
+        t = self.grad[o:o + n]
+        return t.view(shape) if shape is not None else (t.view(p.shape) if numel is None else t)
+
+    def refresh_shadow(self):
+        ops.cast_bf16(self.master[:self.w_end], self.shadow)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the engine: static buffers + hand-scheduled kernel sequence
+# ---------------------------------------------------------------------------------------------------------------------
+class _Plan:
+    """Everything that depends on the batch geometry: buffers, and the captured forward / backward graphs."""
+
+    def __init__(self, eng: "_Engine", key):
+        self.eng = eng
+        (self.B, self.T, self.R, self.C, self.has_tmask, self.has_vmask, self.has_types, self.has_labels,
+         self.dropout, self.need_grad) = key
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.fwd_graph = None
+        self.bwd_graph = None
+        self.fwd_runs = 0
+        self.bwd_runs = 0
+        self.fwd_id = 0
+        dev = eng.flat.device
+        self.s_v = torch.cuda.Stream(device=dev)
+        cfg = eng.cfg
+        B, T, R = self.B, self.T, self.R
+        self.Mt, self.Mv = B * T, B * R
+        i32, f32 = torch.int32, torch.float32
+        self.ids = self.buf("in.ids", (self.Mt,), i32)
+        self.types = self.buf("in.types", (self.Mt,), i32) if self.has_types else None
+        self.labels = self.buf("in.labels", (B,), i32) if self.has_labels else None
+        self.t_bias = self.buf("in.t_bias", (B, T), f32) if self.has_tmask else None
+        self.v_bias = self.buf("in.v_bias", (B, R), f32) if self.has_vmask else None
+        self.feat = self.buf("in.feat", (self.Mv, cfg["v_feature_size"]))
+        self.loc = self.buf("in.loc", (self.Mv, cfg["v_loc_size"]), f32)
+        self.logits = self.buf("out.logits", (B, self.C), f32)
+        self.probs = self.buf("out.probs", (B, self.C), f32)
+        self.loss = self.buf("out.loss", (1,), f32)
+        self.dloss = self.buf("in.dloss", (1,), f32)
+        self.dlogits = self.buf("in.dlogits", (B, self.C), f32)
+
+    def buf(self, name, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None:
+            t = torch.zeros(shape, dtype=dtype, device=self.eng.flat.device)
+            self.bufs[name] = t
+        assert tuple(t.shape) == tuple(shape) and t.dtype == dtype, (name, t.shape, shape)
+        return t
+
+
+class _Engine:
+    def __init__(self, model: "ViLBERTForClassification", device):
+        self.model = model
+        self.cfg = model.config
+        self.flat = _FlatParams(model, device)
+        self.plans: Dict[Any, _Plan] = {}
+        self.seed = torch.tensor([int(os.environ.get("VB_SEED", "20260101"))], dtype=torch.int64, device=device)
+        self.use_graphs = os.environ.get("VB_NO_GRAPH", "0") != "1"
+        self.two_streams = os.environ.get("VB_ONE_STREAM", "0") != "1"
+        self.launches = 0
+        self.grad_hook = None      # data-parallel: called inside backward as hook(flat_grad_range_lo, hi)
+        self._site = 0
+        f = self.flat
+        for p in [f"bert.encoder.layer.{i}.attention.self" for i in range(self.cfg["num_hidden_layers"])] + \
+                 [f"bert.encoder.v_layer.{i}.attention.self" for i in range(self.cfg["v_num_hidden_layers"])]:
+            f.check_contiguous([p + ".query.weight", p + ".key.weight", p + ".value.weight"])
+            f.check_contiguous([p + ".query.bias", p + ".key.bias", p + ".value.bias"])
+        for i in range(self.cfg["num_co_attention_layers"]):
+            p = f"bert.encoder.c_layer.{i}.biattention"
+            for s in ("1", "2"):
+                f.check_contiguous([f"{p}.query{s}.weight", f"{p}.key{s}.weight", f"{p}.value{s}.weight"])
+                f.check_contiguous([f"{p}.query{s}.bias", f"{p}.key{s}.bias", f"{p}.value{s}.bias"])
+
+    # ------------------------------------------------------------------------------------------------ primitives
+    def _linear(self, x, wkey, out, *, rows=None, act=ops.ACT_NONE, preact=None):
+        f = self.flat
+        w = f.w(wkey, rows)
+        bkey = wkey[:-len("weight")] + "bias"
+        ops.gemm(x, w, out, bias=f.m(bkey, w.shape[0]), act=act, preact=preact)
+
+    def _linear_bwd(self, dy, x, wkey, *, rows=None, dx=None, aux=None, aux_mode=ops.AUX_NONE, bias_grad=True):
+        """dW = dy^T x (fp32, straight into the flat gradient buffer), db = colsum(dy) unless already produced by the
+        kernel that made dy, dx = dy W (+ aux | * gelu'(aux))."""
+        f = self.flat
+        w = f.w(wkey, rows)
+        ops.gemm(dy, x, f.g(wkey, shape=tuple(w.shape), numel=w.numel()), a_mn_major=True, b_mn_major=True)
+        if bias_grad:
+            bkey = wkey[:-len("weight")] + "bias"
+            ops.colsum(dy, f.g(bkey, numel=w.shape[0]))
+        if dx is not None:
+            ops.gemm(dy, w, dx, b_mn_major=True, aux=aux, aux_mode=aux_mode)
+
+    def _ln(self, pl, x, res, lnkey, y, tag, p_in=0.0, p_out=0.0):
+        f = self.flat
+        mean, rstd = pl.buf(tag + ".mean", (x.shape[0],), torch.float32), pl.buf(tag + ".rstd", (x.shape[0],), torch.float32)
+        site = self._next_site()
+        drop = pl.dropout
+        ops.layernorm_fwd(x, res, f.m(lnkey + ".weight"), f.m(lnkey + ".bias"), y, mean, rstd,
+                          p_in=p_in if drop else 0.0, site_in=site, p_out=p_out if drop else 0.0, site_out=site + 1,
+                          seed=self.seed if drop else None)
+        return (mean, rstd, site)
+
+    def _ln_bwd(self, pl, dy, x, res, lnkey, saved, *, dx, dres, bias_key=None, p_in=0.0, p_out=0.0):
+        f = self.flat
+        mean, rstd, site = saved
+        drop = pl.dropout
+        ops.layernorm_bwd(dy, x, res, f.m(lnkey + ".weight"), mean, rstd, dx=dx, dres=dres,
+                          dgamma=f.g(lnkey + ".weight"), dbeta=f.g(lnkey + ".bias"),
+                          dbias=f.g(bias_key) if bias_key else None,
+                          p_in=p_in if drop else 0.0, site_in=site, p_out=p_out if drop else 0.0, site_out=site + 1,
+                          seed=self.seed if drop else None)
+
+    def _next_site(self):
+        self._site += 2
+        return self._site
+
+    # ------------------------------------------------------------------------------------------------ layers
+    def _bert_layer_fwd(self, pl, p, tag, x, M, S, H, heads, inter, bias, p_hidden, p_attn):
+        """BertLayer.forward (reference :215-219)."""
+        sv = {}
+        qkv = pl.buf(tag + ".qkv", (M, 3 * H))
+        self._linear(x, p + ".attention.self.query.weight", qkv, rows=3 * H)
+        ctx = pl.buf(tag + ".ctx", (M, H))
+        lse = pl.buf(tag + ".lse", (pl.B, heads, 128), torch.float32)
+        sv["attn_site"] = self._next_site()
+        ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, lse, batch=pl.B, heads=heads, sq=S, sk=S,
+                          d=H // heads, mask_bias=bias, p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"],
+                          seed=self.seed if pl.dropout else None)
+        ao = pl.buf(tag + ".ao", (M, H))
+        self._linear(ctx, p + ".attention.output.dense.weight", ao)
+        a = pl.buf(tag + ".a", (M, H))
+        sv["ln1"] = self._ln(pl, ao, x, p + ".attention.output.LayerNorm", a, tag + ".ln1", p_in=p_hidden)
+        pre = pl.buf(tag + ".pre", (M, inter)) if pl.need_grad else None
+        it = pl.buf(tag + ".int", (M, inter))
+        self._linear(a, p + ".intermediate.dense.weight", it, act=ops.ACT_GELU, preact=pre)
+        fo = pl.buf(tag + ".fo", (M, H))
+        self._linear(it, p + ".output.dense.weight", fo)
+        y = pl.buf(tag + ".y", (M, H))
+        sv["ln2"] = self._ln(pl, fo, a, p + ".output.LayerNorm", y, tag + ".ln2", p_in=p_hidden)
+        sv.update(x=x, qkv=qkv, ctx=ctx, lse=lse, ao=ao, a=a, pre=pre, it=it, fo=fo, y=y)
+        return y, sv
+
+    def _ffn_bwd(self, pl, pfx_int, pfx_out, lnkey, sv_ln, dy, fo, a, pre, it, M, H, inter, sc, p_hidden):
+        """Backward of  y = LN(drop(dense_out(gelu(dense_int(a)))) + a);  returns grad wrt a."""
+        g_fo = pl.buf(sc + ".g_fo", (M, H))
+        g_ares = pl.buf(sc + ".g_ares", (M, H)) if pl.dropout else None
+        self._ln_bwd(pl, dy, fo, a, lnkey, sv_ln, dx=g_fo, dres=g_ares, bias_key=pfx_out + ".bias", p_in=p_hidden)
+        g_pre = pl.buf(sc + ".g_pre", (M, inter))
+        self._linear_bwd(g_fo, it, pfx_out + ".weight", dx=g_pre, aux=pre, aux_mode=ops.AUX_MUL_GELU_GRAD, bias_grad=False)
+        g_a = pl.buf(sc + ".g_a", (M, H))
+        self._linear_bwd(g_pre, a, pfx_int + ".weight", dx=g_a, aux=g_ares if g_ares is not None else g_fo, aux_mode=ops.AUX_ADD)
+        return g_a
+
+    def _bert_layer_bwd(self, pl, p, sv, dy, dx_out, M, S, H, heads, inter, bias, p_hidden, p_attn, sc):
+        g_a = self._ffn_bwd(pl, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", sv["ln2"], dy,
+                            sv["fo"], sv["a"], sv["pre"], sv["it"], M, H, inter, sc, p_hidden)
+        g_ao = pl.buf(sc + ".g_ao", (M, H))
+        g_xres = pl.buf(sc + ".g_xres", (M, H)) if pl.dropout else None
+        self._ln_bwd(pl, g_a, sv["ao"], sv["x"], p + ".attention.output.LayerNorm", sv["ln1"], dx=g_ao, dres=g_xres,
+                     bias_key=p + ".attention.output.dense.bias", p_in=p_hidden)
+        g_ctx = pl.buf(sc + ".g_ctx", (M, H))
+        self._linear_bwd(g_ao, sv["ctx"], p + ".attention.output.dense.weight", dx=g_ctx, bias_grad=False)
+        g_qkv = pl.buf(sc + ".g_qkv", (M, 3 * H))
+        qkv = sv["qkv"]
+        ops.attention_bwd(g_ctx, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["lse"], g_qkv[:, :H], g_qkv[:, H:2 * H],
+                          g_qkv[:, 2 * H:], batch=pl.B, heads=heads, sq=S, sk=S, d=H // heads, mask_bias=bias,
+                          p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"], seed=self.seed if pl.dropout else None)
+        self._linear_bwd(g_qkv, sv["x"], p + ".attention.self.query.weight", rows=3 * H, dx=dx_out,
+                         aux=g_xres if g_xres is not None else g_ao, aux_mode=ops.AUX_ADD)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def run_forward(self, pl: _Plan):
+        cfg, f = self.cfg, self.flat
+        self._site = 0
+        H, Hv, bi = cfg["hidden_size"], cfg["v_hidden_size"], cfg["bi_hidden_size"]
+        I, Iv = cfg["intermediate_size"], cfg["v_intermediate_size"]
+        nh, nhv = cfg["num_attention_heads"], cfg["v_num_attention_heads"]
+        ph, pa = cfg["hidden_dropout_prob"], cfg["attention_probs_dropout_prob"]
+        pvh = cfg["v_hidden_dropout_prob"]
+        B, T, R, Mt, Mv = pl.B, pl.T, pl.R, pl.Mt, pl.Mv
+        s_t = torch.cuda.current_stream()
+        s_v = pl.s_v if self.two_streams else s_t
+        sv = pl.saved = {}
+        if pl.dropout:
+            ops.seed_advance(self.seed)
+        s_v.wait_stream(s_t)
+
+        # text embeddings (transformers BertEmbeddings) | visual embeddings (reference :100-104)
+        t = pl.buf("emb.t", (Mt, H))
+        e = "bert.embeddings"
+        mean, rstd = pl.buf("emb.mean", (Mt,), torch.float32), pl.buf("emb.rstd", (Mt,), torch.float32)
+        sv["emb_site"] = self._next_site()
+        ops.embed_text_fwd(pl.ids, pl.types, f.m(e + ".word_embeddings.weight").view(-1, H),
+                           f.m(e + ".position_embeddings.weight").view(-1, H),
+                           f.m(e + ".token_type_embeddings.weight").view(-1, H), f.m(e + ".LayerNorm.weight"),
+                           f.m(e + ".LayerNorm.bias"), t, mean, rstd, B, T, p_out=ph if pl.dropout else 0.0,
+                           site_out=sv["emb_site"], seed=self.seed if pl.dropout else None)
+        with torch.cuda.stream(s_v):
+            ve = "bert.v_embeddings"
+            img = pl.buf("vemb.img", (Mv, Hv))
+            self._linear(pl.feat, ve + ".image_embeddings.weight", img)
+            loc = pl.buf("vemb.loc", (Mv, Hv))
+            ops.loc_embed_fwd(pl.loc, f.m(ve + ".image_location_embeddings.weight").view(Hv, -1),
+                              f.m(ve + ".image_location_embeddings.bias"), loc)
+            v = pl.buf("vemb.v", (Mv, Hv))
+            sv["vemb_ln"] = self._ln(pl, img, loc, ve + ".LayerNorm", v, "vemb.ln", p_out=pvh)
+
+        c = 0
+        for i in range(cfg["num_hidden_layers"]):
+            t, sv[f"t{i}"] = self._bert_layer_fwd(pl, f"bert.encoder.layer.{i}", f"t{i}", t, Mt, T, H, nh, I, pl.t_bias, ph, ph)
+            if i in CO_ATTENTION_TEXT_LAYERS and c < cfg["num_co_attention_layers"]:
+                with torch.cuda.stream(s_v):
+                    # the reference hands ONE dropout_prob (v_hidden_dropout_prob) to the visual BertLayer (:441-446)
+                    v, sv[f"v{c}"] = self._bert_layer_fwd(pl, f"bert.encoder.v_layer.{c}", f"v{c}", v, Mv, R, Hv, nhv, Iv,
+                                                         pl.v_bias, pvh, pvh)
+                v, t, sv[f"c{c}"] = self._co_layer_fwd(pl, c, v, t, s_t, s_v)
+                c += 1
+        s_t.wait_stream(s_v)
+
+        # poolers (:404-408), concat, classifier (:569-578), CE (:637-639)
+        pooled = pl.buf("head.pooled", (B, bi + Hv))
+        ops.gemm(t.view(B, T * H)[:, :H], f.w("bert.t_pooler.dense.weight"), pooled[:, :bi],
+                 bias=f.m("bert.t_pooler.dense.bias"), act=ops.ACT_TANH)
+        ops.gemm(v.view(B, R * Hv)[:, :Hv], f.w("bert.v_pooler.dense.weight"), pooled[:, bi:],
+                 bias=f.m("bert.v_pooler.dense.bias"), act=ops.ACT_TANH)
+        sv["head_site"] = self._next_site()
+        pooled_d = pooled
+        if pl.dropout:
+            pooled_d = ops.dropout(pooled, pl.buf("head.pooled_d", (B, bi + Hv)), 0.1, sv["head_site"], self.seed)
+        hid = pl.buf("head.hid", (B, bi))
+        ops.gemm(pooled_d, f.w("classifier.1.weight"), hid, bias=f.m("classifier.1.bias"), act=ops.ACT_RELU)
+        hid_d = hid
+        if pl.dropout:
+            hid_d = ops.dropout(hid, pl.buf("head.hid_d", (B, bi)), 0.1, sv["head_site"] + 1, self.seed)
+        ops.cls_ce_fwd(hid_d, f.m("classifier.4.weight").view(pl.C, bi), f.m("classifier.4.bias"), pl.labels, pl.logits,
+                       pl.probs, pl.loss)
+        sv.update(t_final=t, v_final=v, pooled=pooled, pooled_d=pooled_d, hid=hid, hid_d=hid_d)
+
+    def _co_layer_fwd(self, pl, c, v, t, s_t, s_v):
+        """CoAttentionLayer.forward (reference :377-394): BiAttention :253-294, BiOutput :324-338, two FFNs."""
+        cfg = self.cfg
+        H, Hv, bi = cfg["hidden_size"], cfg["v_hidden_size"], cfg["bi_hidden_size"]
+        I, Iv = cfg["intermediate_size"], cfg["v_intermediate_size"]
+        heads = cfg["v_num_attention_heads"]
+        d = bi // heads
+        ph, pa, pvh = cfg["hidden_dropout_prob"], cfg["attention_probs_dropout_prob"], cfg["v_hidden_dropout_prob"]
+        B, T, R, Mt, Mv = pl.B, pl.T, pl.R, pl.Mt, pl.Mv
+        p, tag = f"bert.encoder.c_layer.{c}", f"c{c}"
+        drop = pl.dropout
+        sv = {"v_in": v, "t_in": t}
+        tqkv = pl.buf(tag + ".tqkv", (Mt, 3 * bi))
+        self._linear(t, p + ".biattention.query2.weight", tqkv, rows=3 * bi)
+        with torch.cuda.stream(s_v):
+            vqkv = pl.buf(tag + ".vqkv", (Mv, 3 * bi))
+            self._linear(v, p + ".biattention.query1.weight", vqkv, rows=3 * bi)
+        s_t.wait_stream(s_v)
+        s_v.wait_stream(s_t)
+        sv["site_v"], sv["site_t"] = self._next_site(), self._next_site()
+        # text FFN half on the text stream
+        t_ctx = pl.buf(tag + ".t_ctx", (Mt, bi))
+        t_lse = pl.buf(tag + ".t_lse", (B, heads, 128), torch.float32)
+        ops.attention_fwd(tqkv[:, :bi], vqkv[:, bi:2 * bi], vqkv[:, 2 * bi:], t_ctx, t_lse, batch=B, heads=heads, sq=T,
+                          sk=R, d=d, mask_bias=pl.v_bias, p_drop=pa if drop else 0.0, site=sv["site_t"],
+                          seed=self.seed if drop else None)
+        t_bo = pl.buf(tag + ".t_bo", (Mt, H))
+        self._linear(t_ctx, p + ".biOutput.dense2.weight", t_bo)
+        t_att = pl.buf(tag + ".t_att", (Mt, H))
+        sv["t_ln1"] = self._ln(pl, t_bo, t, p + ".biOutput.LayerNorm2", t_att, tag + ".t_ln1", p_in=ph)
+        t_pre = pl.buf(tag + ".t_pre", (Mt, I)) if pl.need_grad else None
+        t_int = pl.buf(tag + ".t_int", (Mt, I))
+        self._linear(t_att, p + ".t_intermediate.dense.weight", t_int, act=ops.ACT_GELU, preact=t_pre)
+        t_fo = pl.buf(tag + ".t_fo", (Mt, H))
+        self._linear(t_int, p + ".t_output.dense.weight", t_fo)
+        t_out = pl.buf(tag + ".t_out", (Mt, H))
+        sv["t_ln2"] = self._ln(pl, t_fo, t_att, p + ".t_output.LayerNorm", t_out, tag + ".t_ln2", p_in=ph)
+        with torch.cuda.stream(s_v):
+            v_ctx = pl.buf(tag + ".v_ctx", (Mv, bi))
+            v_lse = pl.buf(tag + ".v_lse", (B, heads, 128), torch.float32)
+            ops.attention_fwd(vqkv[:, :bi], tqkv[:, bi:2 * bi], tqkv[:, 2 * bi:], v_ctx, v_lse, batch=B, heads=heads, sq=R,
+                              sk=T, d=d, mask_bias=pl.t_bias, p_drop=pa if drop else 0.0, site=sv["site_v"],
+                              seed=self.seed if drop else None)
+            v_bo = pl.buf(tag + ".v_bo", (Mv, Hv))
+            self._linear(v_ctx, p + ".biOutput.dense1.weight", v_bo)
+            v_att = pl.buf(tag + ".v_att", (Mv, Hv))
+            sv["v_ln1"] = self._ln(pl, v_bo, v, p + ".biOutput.LayerNorm1", v_att, tag + ".v_ln1", p_in=ph)
+            v_pre = pl.buf(tag + ".v_pre", (Mv, Iv)) if pl.need_grad else None
+            v_int = pl.buf(tag + ".v_int", (Mv, Iv))
+            self._linear(v_att, p + ".v_intermediate.dense.weight", v_int, act=ops.ACT_GELU, preact=v_pre)
+            v_fo = pl.buf(tag + ".v_fo", (Mv, Hv))
+            self._linear(v_int, p + ".v_output.dense.weight", v_fo)
+            v_out = pl.buf(tag + ".v_out", (Mv, Hv))
+            sv["v_ln2"] = self._ln(pl, v_fo, v_att, p + ".v_output.LayerNorm", v_out, tag + ".v_ln2", p_in=pvh)
+        sv.update(tqkv=tqkv, vqkv=vqkv, t_ctx=t_ctx, t_lse=t_lse, t_bo=t_bo, t_att=t_att, t_pre=t_pre, t_int=t_int,
+                  t_fo=t_fo, t_out=t_out, v_ctx=v_ctx, v_lse=v_lse, v_bo=v_bo, v_att=v_att, v_pre=v_pre, v_int=v_int,
+                  v_fo=v_fo, v_out=v_out)
+        return v_out, t_out, sv
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def run_backward(self, pl: _Plan):
+        cfg, f = self.cfg, self.flat
+        H, Hv, bi = cfg["hidden_size"], cfg["v_hidden_size"], cfg["bi_hidden_size"]
+        I, Iv = cfg["intermediate_size"], cfg["v_intermediate_size"]
+        nh, nhv = cfg["num_attention_heads"], cfg["v_num_attention_heads"]
+        ph, pa, pvh = cfg["hidden_dropout_prob"], cfg["attention_probs_dropout_prob"], cfg["v_hidden_dropout_prob"]
+        B, T, R, Mt, Mv = pl.B, pl.T, pl.R, pl.Mt, pl.Mv
+        sv = pl.saved
+        s_t = torch.cuda.current_stream()
+        s_v = pl.s_v if self.two_streams else s_t
+        # gradients that are accumulated with atomics start from zero (biases, LayerNorm, location weights, tables)
+        f.grad[f.w_end:f.s_end].zero_()
+        dy_t = [pl.buf("g.t_ping", (Mt, H)), pl.buf("g.t_pong", (Mt, H))]
+        dy_v = [pl.buf("g.v_ping", (Mv, Hv)), pl.buf("g.v_pong", (Mv, Hv))]
+        dy_t[0].zero_()
+        dy_v[0].zero_()
+
+        # head
+        g_hid_d = pl.buf("g.hid_d", (B, bi))
+        ops.cls_ce_bwd(sv["hid_d"], f.m("classifier.4.weight").view(pl.C, bi), pl.labels, pl.probs, pl.dloss, pl.dlogits,
+                       f.g("classifier.4.weight"), f.g("classifier.4.bias"), g_hid_d)
+        g_hid = g_hid_d
+        if pl.dropout:
+            g_hid = ops.dropout(g_hid_d, pl.buf("g.hid", (B, bi)), 0.1, sv["head_site"] + 1, self.seed)
+        g_hid_pre = ops.act_bwd(g_hid, sv["hid"], pl.buf("g.hid_pre", (B, bi)), ops.ACT_RELU)
+        g_pooled_d = pl.buf("g.pooled_d", (B, bi + Hv))
+        self._linear_bwd(g_hid_pre, sv["pooled_d"], "classifier.1.weight", dx=g_pooled_d)
+        g_pooled = g_pooled_d
+        if pl.dropout:
+            g_pooled = ops.dropout(g_pooled_d, pl.buf("g.pooled", (B, bi + Hv)), 0.1, sv["head_site"], self.seed)
+        g_pool_pre = ops.act_bwd(g_pooled, sv["pooled"], pl.buf("g.pool_pre", (B, bi + Hv)), ops.ACT_TANH)
+        s_v.wait_stream(s_t)
+        self._linear_bwd(g_pool_pre[:, :bi], sv["t_final"].view(B, T * H)[:, :H], "bert.t_pooler.dense.weight",
+                         dx=dy_t[0].view(B, T * H)[:, :H])
+        with torch.cuda.stream(s_v):
+            self._linear_bwd(g_pool_pre[:, bi:], sv["v_final"].view(B, R * Hv)[:, :Hv], "bert.v_pooler.dense.weight",
+                             dx=dy_v[0].view(B, R * Hv)[:, :Hv])
+
+        # encoder, reversed
+        it_, iv_ = 0, 0   # which ping/pong buffer currently holds the incoming gradient
+        n_co = min(cfg["num_co_attention_layers"], sum(1 for i in range(cfg["num_hidden_layers"]) if i in CO_ATTENTION_TEXT_LAYERS))
+        c = n_co
+        for i in reversed(range(cfg["num_hidden_layers"])):
+            if i in CO_ATTENTION_TEXT_LAYERS and c > 0 and self._co_index(i) < n_co:
+                c -= 1
+                self._co_layer_bwd(pl, c, sv[f"c{c}"], dy_v[iv_], dy_t[it_], dy_v[1 - iv_], dy_t[1 - it_], s_t, s_v)
+                iv_, it_ = 1 - iv_, 1 - it_
+                with torch.cuda.stream(s_v):
+                    self._bert_layer_bwd(pl, f"bert.encoder.v_layer.{c}", sv[f"v{c}"], dy_v[iv_], dy_v[1 - iv_], Mv, R, Hv,
+                                         nhv, Iv, pl.v_bias, pvh, pvh, "gv")
+                iv_ = 1 - iv_
+            self._bert_layer_bwd(pl, f"bert.encoder.layer.{i}", sv[f"t{i}"], dy_t[it_], dy_t[1 - it_], Mt, T, H, nh, I,
+                                 pl.t_bias, ph, ph, "gt")
+            it_ = 1 - it_
+
+        # embeddings
+        with torch.cuda.stream(s_v):
+            ve = "bert.v_embeddings"
+            g_s = pl.buf("g.vemb_s", (Mv, Hv))
+            self._ln_bwd(pl, dy_v[iv_], pl.bufs["vemb.img"], pl.bufs["vemb.loc"], ve + ".LayerNorm", sv["vemb_ln"], dx=g_s,
+                         dres=None, bias_key=ve + ".image_embeddings.bias", p_out=pvh)
+            self._linear_bwd(g_s, pl.feat, ve + ".image_embeddings.weight", bias_grad=False)
+            ops.loc_embed_bwd(g_s, pl.loc, f.g(ve + ".image_location_embeddings.weight"),
+                              f.g(ve + ".image_location_embeddings.bias"))
+        e = "bert.embeddings"
+        ops.embed_text_bwd(dy_t[it_], pl.ids, pl.types, f.m(e + ".word_embeddings.weight").view(-1, H),
+                           f.m(e + ".position_embeddings.weight").view(-1, H),
+                           f.m(e + ".token_type_embeddings.weight").view(-1, H), f.m(e + ".LayerNorm.weight"),
+                           pl.bufs["emb.mean"], pl.bufs["emb.rstd"], B, T,
+                           dword=f.g(e + ".word_embeddings.weight"), dpos=f.g(e + ".position_embeddings.weight"),
+                           dtype=f.g(e + ".token_type_embeddings.weight"), dgamma=f.g(e + ".LayerNorm.weight"),
+                           dbeta=f.g(e + ".LayerNorm.bias"), p_out=ph if pl.dropout else 0.0, site_out=sv["emb_site"],
+                           seed=self.seed if pl.dropout else None)
+        s_t.wait_stream(s_v)
+
+    @staticmethod
+    def _co_index(text_layer):
+        return CO_ATTENTION_TEXT_LAYERS.index(text_layer)
+
+    def _co_layer_bwd(self, pl, c, sv, dv, dt, dv_out, dt_out, s_t, s_v):
+        cfg = self.cfg
+        H, Hv, bi = cfg["hidden_size"], cfg["v_hidden_size"], cfg["bi_hidden_size"]
+        I, Iv = cfg["intermediate_size"], cfg["v_intermediate_size"]
+        heads = cfg["v_num_attention_heads"]
+        d = bi // heads
+        ph, pa, pvh = cfg["hidden_dropout_prob"], cfg["attention_probs_dropout_prob"], cfg["v_hidden_dropout_prob"]
+        B, T, R, Mt, Mv = pl.B, pl.T, pl.R, pl.Mt, pl.Mv
+        p = f"bert.encoder.c_layer.{c}"
+        drop = pl.dropout
+        seed = self.seed if drop else None
+        g_tqkv = pl.buf(f"gc{c & 1}.tqkv", (Mt, 3 * bi))  # double-buffered: written from both streams
+        g_vqkv = pl.buf(f"gc{c & 1}.vqkv", (Mv, 3 * bi))
+        tqkv, vqkv = sv["tqkv"], sv["vqkv"]
+        # text half down to the gradient of t_ctx
+        g_tatt = self._ffn_bwd(pl, p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", sv["t_ln2"],
+                               dt, sv["t_fo"], sv["t_att"], sv["t_pre"], sv["t_int"], Mt, H, I, "gct", ph)
+        g_tbo = pl.buf("gct.g_bo", (Mt, H))
+        g_tres = pl.buf("gct.g_res", (Mt, H)) if drop else None
+        self._ln_bwd(pl, g_tatt, sv["t_bo"], sv["t_in"], p + ".biOutput.LayerNorm2", sv["t_ln1"], dx=g_tbo, dres=g_tres,
+                     bias_key=p + ".biOutput.dense2.bias", p_in=ph)
+        g_tctx = pl.buf("gct.g_ctx", (Mt, bi))
+        self._linear_bwd(g_tbo, sv["t_ctx"], p + ".biOutput.dense2.weight", dx=g_tctx, bias_grad=False)
+        with torch.cuda.stream(s_v):
+            g_vatt = self._ffn_bwd(pl, p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm",
+                                   sv["v_ln2"], dv, sv["v_fo"], sv["v_att"], sv["v_pre"], sv["v_int"], Mv, Hv, Iv, "gcv", pvh)
+            g_vbo = pl.buf("gcv.g_bo", (Mv, Hv))
+            g_vres = pl.buf("gcv.g_res", (Mv, Hv)) if drop else None
+            self._ln_bwd(pl, g_vatt, sv["v_bo"], sv["v_in"], p + ".biOutput.LayerNorm1", sv["v_ln1"], dx=g_vbo, dres=g_vres,
+                         bias_key=p + ".biOutput.dense1.bias", p_in=ph)
+            g_vctx = pl.buf("gcv.g_ctx", (Mv, bi))
+            self._linear_bwd(g_vbo, sv["v_ctx"], p + ".biOutput.dense1.weight", dx=g_vctx, bias_grad=False)
+            # regions attend to tokens: dq -> visual q1, dk/dv -> text k2/v2
+            ops.attention_bwd(g_vctx, vqkv[:, :bi], tqkv[:, bi:2 * bi], tqkv[:, 2 * bi:], sv["v_lse"], g_vqkv[:, :bi],
+                              g_tqkv[:, bi:2 * bi], g_tqkv[:, 2 * bi:], batch=B, heads=heads, sq=R, sk=T, d=d,
+                              mask_bias=pl.t_bias, p_drop=pa if drop else 0.0, site=sv["site_v"], seed=seed)
+        # tokens attend to regions: dq -> text q2, dk/dv -> visual k1/v1
+        ops.attention_bwd(g_tctx, tqkv[:, :bi], vqkv[:, bi:2 * bi], vqkv[:, 2 * bi:], sv["t_lse"], g_tqkv[:, :bi],
+                          g_vqkv[:, bi:2 * bi], g_vqkv[:, 2 * bi:], batch=B, heads=heads, sq=T, sk=R, d=d,
+                          mask_bias=pl.v_bias, p_drop=pa if drop else 0.0, site=sv["site_t"], seed=seed)
+        s_t.wait_stream(s_v)
+        s_v.wait_stream(s_t)
+        self._linear_bwd(g_tqkv, sv["t_in"], p + ".biattention.query2.weight", rows=3 * bi, dx=dt_out,
+                         aux=g_tres if g_tres is not None else g_tbo, aux_mode=ops.AUX_ADD)
+        with torch.cuda.stream(s_v):
+            self._linear_bwd(g_vqkv, sv["v_in"], p + ".biattention.query1.weight", rows=3 * bi, dx=dv_out,
+                             aux=g_vres if g_vres is not None else g_vbo, aux_mode=ops.AUX_ADD)
+
+    # ------------------------------------------------------------------------------------------------ execution
+    def _execute(self, pl: _Plan, which: str):
+        fn = self.run_forward if which == "fwd" else self.run_backward
+        runs = pl.fwd_runs if which == "fwd" else pl.bwd_runs
+        graph = pl.fwd_graph if which == "fwd" else pl.bwd_graph
+        if which == "fwd":
+            pl.fwd_runs += 1
+        else:
+            pl.bwd_runs += 1
+        if not self.use_graphs or runs == 0:
+            fn(pl)  # eager (also the warm-up that loads modules / sets function attributes before any capture)
+            return
+        if graph is None:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                fn(pl)
+            if which == "fwd":
+                pl.fwd_graph = graph
+            else:
+                pl.bwd_graph = graph
+        graph.replay()
+
+
+class _Step(torch.autograd.Function):
+    """One node in the autograd graph for the whole model: forward returns (logits, loss); backward runs the
+    hand-written backward pass and deposits fp32 gradients on the parameters (views of the flat gradient buffer)."""
+
+    @staticmethod
+    def forward(ctx, anchor, module, plan):
+        eng = module._engine
+        eng._execute(plan, "fwd")
+        plan.fwd_id += 1
+        ctx.module, ctx.plan, ctx.fwd_id = module, plan, plan.fwd_id
+        return plan.logits.clone(), plan.loss[0].clone()
+
+    @staticmethod
+    def backward(ctx, g_logits, g_loss):
+        module, plan = ctx.module, ctx.plan
+        eng = module._engine
+        if plan.fwd_id != ctx.fwd_id:
+            raise VbError("backward() of a forward whose saved activations were overwritten by a later forward of the "
+                          "same shape; call backward before the next forward")
+        if g_logits is None:
+            plan.dlogits.zero_()
+        else:
+            plan.dlogits.copy_(g_logits)
+        if g_loss is None:
+            plan.dloss.zero_()
+        else:
+            plan.dloss.copy_(g_loss.reshape(1))
+        flat = eng.flat
+        carry = None
+        params = module._trainable_used()
+        if any(p.grad is not None for _, p in params):
+            carry = {k: p.grad.clone() for k, p in params if p.grad is not None}   # gradient accumulation (rare path)
+        eng._execute(plan, "bwd")
+        if eng.grad_hook is not None:
+            eng.grad_hook()
+        for k, p in params:
+            g = flat.g(k)
+            if carry is not None and k in carry:
+                g.add_(carry[k])
+            p.grad = g
+        return None, None, None
+
+
+class ViLBERTForClassification(nn.Module):
+    """Drop-in for the reference class of the same name (vilbert_facebook_arch.py:554-641): same constructor, same
+    parameter names / shapes / ``state_dict``, same keyword ``forward`` returning ``{"logits", "loss"?}``, same
+    ``get_num_parameters`` / ``freeze_bert_layers``.  CUDA only: a forward on CPU tensors raises."""
+
+    def __init__(self, config: Dict[str, Any], num_labels: int = 2):
+        super().__init__()
+        self.config = config
+        self.num_labels = num_labels
+        self.bert = _Backbone(config)
+        cls_in = config["bi_hidden_size"] + config["v_hidden_size"]
+        self.classifier = nn.Sequential(nn.Dropout(0.1), nn.Linear(cls_in, config["bi_hidden_size"]), nn.ReLU(),
+                                        nn.Dropout(0.1), nn.Linear(config["bi_hidden_size"], num_labels))
+        self._engine: Optional[_Engine] = None
+        self._anchor = None
+        if config["bi_hidden_size"] != config["v_hidden_size"]:
+            raise VbError("bi_hidden_size must equal v_hidden_size (as in the reference's v_pooler / BiOutput)")
+
+    # -- reference surface ------------------------------------------------------------------------------------------
+    def get_num_parameters(self) -> Tuple[int, int]:
+        total = sum(p.numel() for p in self.parameters())
+        trainable = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return total, trainable
+
+    def freeze_bert_layers(self, num_layers: int = 6) -> None:
+        """Reference :586-608: freeze text embeddings and the first N text layers."""
+        if num_layers <= 0:
+            return
+        for p in self.bert.embeddings.parameters():
+            p.requires_grad = False
+        for i, layer in enumerate(self.bert.encoder.layer):
+            if i < num_layers:
+                for p in layer.parameters():
+                    p.requires_grad = False
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._engine = None   # parameters were re-created (device / dtype move): re-flatten lazily
+        return out
+
+    def _trainable_used(self):
+        eng = self._engine
+        return [(k, p) for k, p in eng.flat.named.items() if p.requires_grad and k in eng.flat.used]
+
+    def _ensure_engine(self, device) -> _Engine:
+        eng = self._engine
+        if eng is not None and (not eng.flat.intact() or eng.flat.device != device):
+            eng = None
+        if eng is None:
+            for p in self.parameters():
+                if p.device != device:
+                    raise VbError(f"parameter on {p.device}, inputs on {device}: call model.to(device) first")
+                if p.dtype != torch.float32:
+                    raise VbError("parameters must stay fp32 (bf16 shadows are kept internally)")
+            eng = self._engine = _Engine(self, device)
+            self._anchor = torch.zeros(1, device=device, requires_grad=True)
+        ver = eng.flat.versions()
+        if ver != eng.flat._version:
+            eng.flat.refresh_shadow()
+            eng.flat._version = ver
+        return eng
+
+    def forward(self, input_ids, attention_mask=None, token_type_ids=None, visual_features=None,
+                visual_attention_mask=None, spatial_locations=None, labels=None, *, image_feat=None, image_loc=None,
+                image_attention_mask=None):
+        # aliases named by the north-star signature
+        visual_features = image_feat if visual_features is None else visual_features
+        spatial_locations = image_loc if spatial_locations is None else spatial_locations
+        visual_attention_mask = image_attention_mask if visual_attention_mask is None else visual_attention_mask
+        if visual_features is None or spatial_locations is None:
+            raise VbError("visual_features and spatial_locations are required")
+        if not input_ids.is_cuda:
+            raise VbError("ViLBERTForClassification (B200) runs on CUDA tensors only; there is no CPU fallback")
+        device = input_ids.device
+        cfg = self.config
+        with torch.cuda.device(device):
+            eng = self._ensure_engine(device)
+            B, T = input_ids.shape
+            R = visual_features.shape[1]
+            if T > 128 or R > 128:
+                raise VbError(f"sequence lengths above 128 are not supported by the fused attention (T={T}, R={R})")
+            if visual_features.shape[2] != cfg["v_feature_size"] or spatial_locations.shape[-1] != cfg["v_loc_size"]:
+                raise VbError("visual feature / location width does not match the configuration")
+            need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+            dropout = bool(self.training)
+            key = (B, T, R, self.num_labels, attention_mask is not None, visual_attention_mask is not None,
+                   token_type_ids is not None, labels is not None, dropout, need_grad)
+            pl = eng.plans.get(key)
+            if pl is None:
+                pl = eng.plans[key] = _Plan(eng, key)
+            # stage the batch into the plan's static buffers (the graphs read these addresses)
+            ops.i64_to_i32(input_ids.contiguous(), pl.ids, 0, cfg["vocab_size"]) if input_ids.dtype == torch.int64 \
+                else pl.ids.copy_(input_ids.reshape(-1))
+            if token_type_ids is not None:
+                ops.i64_to_i32(token_type_ids.contiguous(), pl.types, 0, 2) if token_type_ids.dtype == torch.int64 \
+                    else pl.types.copy_(token_type_ids.reshape(-1))
+            if labels is not None:
+                ops.i64_to_i32(labels.contiguous(), pl.labels, 0, self.num_labels) if labels.dtype == torch.int64 \
+                    else pl.labels.copy_(labels.reshape(-1))
+            if attention_mask is not None:
+                ops.mask_bias(attention_mask.contiguous(), pl.t_bias)
+            if visual_attention_mask is not None:
+                ops.mask_bias(visual_attention_mask.contiguous(), pl.v_bias)
+            vf = visual_features.reshape(pl.Mv, -1)
+            if vf.dtype == torch.float32:
+                ops.cast_bf16(vf.contiguous(), pl.feat)
+            else:
+                pl.feat.copy_(vf)
+            pl.loc.copy_(spatial_locations.reshape(pl.Mv, -1))
+            if need_grad:
+                logits, loss = _Step.apply(self._anchor, self, pl)
+            else:
+                eng._execute(pl, "fwd")
+                logits, loss = pl.logits.clone(), pl.loss[0].clone()
+        out = {"logits": logits}
+        if labels is not None:
+            out["loss"] = loss
+        return out
+
+
+def load_facebook_weights(model: ViLBERTForClassification, checkpoint_path: str) -> int:
+    """Same contract as the reference's loader (vilbert_facebook_arch.py:644-683): copy every checkpoint tensor whose key
+    and shape match, ignore the rest, return the number loaded."""
+    state = torch.load(checkpoint_path, map_location="cpu")
+    own = model.state_dict()
+    picked = {k: v for k, v in state.items() if k in own and own[k].shape == v.shape}
+    model.load_state_dict(picked, strict=False)
+    return len(picked)
