@@ -25,7 +25,7 @@ def compare_with_oracle(cfg, batch_kw, tol_logits=2e-2, check_grads=True, verbos
     out["loss"].backward()
     torch.cuda.synchronize()
     ref_out, ref_grads = vo.loss_and_grads(sd, cfg, batch)
-    logits = out["logits"].float().cpu()
+    logits = out["logits"].detach().float().cpu()
     scale = ref_out["logits"].abs().max().item()
     err = (logits - ref_out["logits"]).abs().max().item()
     loss_err = abs(out["loss"].item() - ref_out["loss"].item())

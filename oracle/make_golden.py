@@ -62,6 +62,20 @@ def run_case(name, cfg, batch_kw, seed_w=0):
                 rec[f"grad_{scalar}/{k}"] = p.grad.numpy().copy()
         rec[f"gradnorm_{scalar}"] = np.asarray(norms, dtype=np.float64)
         rec["param_names"] = np.asarray(names)
+    # yardstick: the reference itself under PyTorch's CPU bf16 autocast, same weights and batch — what
+    # bf16 arithmetic costs on this model, measured, so that the GPU tolerances are relative to it and not guessed
+    fp32_grads = {k: rec[f"grad_logit1/{k}"] for k in FULL_GRAD_KEYS if f"grad_logit1/{k}" in rec}
+    fp32_logits = out["logits"].detach().clone()
+    m.zero_grad(set_to_none=True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out_bf = m(**batch)
+        out_bf["logits"].float()[:, 1].sum().backward()
+    rec["yard_logits"] = np.asarray(float((out_bf["logits"].float() - fp32_logits).abs().max() / fp32_logits.abs().max()))
+    params = dict(m.named_parameters())
+    for k, ref in fp32_grads.items():
+        gb = params[k].grad.float().numpy()
+        rec[f"yard_rel_l2/{k}"] = np.asarray(float(np.linalg.norm(gb - ref) / (np.linalg.norm(ref) + 1e-30)))
+    m.zero_grad(set_to_none=True)
     with torch.no_grad():
         t_h, v_h, t_p, v_p = m.bert(**{k: v for k, v in batch.items() if k != "labels"})
     rec.update({"logits": out["logits"].detach().numpy(), "loss": np.asarray(float(out["loss"])),
@@ -70,6 +84,8 @@ def run_case(name, cfg, batch_kw, seed_w=0):
     # eval-set scores for the AUROC-ordering check: softmax(logits)[:,1] on a second, larger synthetic set
     os.makedirs(GOLDEN, exist_ok=True)
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **rec)
+    print(name, "autocast yardstick: logits", float(rec["yard_logits"]), "grad rel-L2",
+          {k.split("/")[1][-40:]: round(float(v), 4) for k, v in rec.items() if k.startswith("yard_rel_l2/")})
     print(name, "logits[0]", rec["logits"][0], "loss", rec["loss"], "max|logit|", np.abs(rec["logits"]).max())
 
 

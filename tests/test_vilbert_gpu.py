@@ -52,7 +52,7 @@ def test_matches_reference_fixtures(name):
     model = _model(cfg)
     batch = {k: v.cuda() for k, v in vo.synthetic_batch(cfg, **kw).items()}
     out = model(**batch)
-    logits = out["logits"].float().cpu().numpy()
+    logits = out["logits"].detach().float().cpu().numpy()
     scale = np.abs(g["logits"]).max()
     assert np.abs(logits - g["logits"]).max() <= 2e-2 * scale, (np.abs(logits - g["logits"]).max(), scale)
     assert abs(out["loss"].item() - float(g["loss"])) <= 1e-3
@@ -61,6 +61,9 @@ def test_matches_reference_fixtures(name):
     rel = _grad_stats(model, g["gradnorm_logit1"], names)
     worst = max(rel)
     assert worst[0] <= 5e-2, worst
+    # full gradients of a few tensors: rel-L2 error against the reference's fp32 gradient, bounded by twice what the
+    # reference itself loses under PyTorch's bf16 autocast on the same batch (yardstick stored with the fixture)
+    report = []
     for key in g.files:
         if key.startswith("grad_logit1/"):
             n = key.split("/", 1)[1]
@@ -68,8 +71,13 @@ def test_matches_reference_fixtures(name):
                 continue
             ref = g[key]
             got = dict(model.named_parameters())[n].grad.float().cpu().numpy()
-            denom = np.abs(ref).max()
-            assert np.abs(got - ref).max() <= 4e-2 * denom + 1e-7, (n, np.abs(got - ref).max(), denom)
+            rel = float(np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30))
+            yard = float(g["yard_rel_l2/" + n])
+            report.append((n, rel, yard))
+            assert rel <= max(2.0 * yard, 3e-2), (n, rel, yard)
+    print("\n".join(f"{n}: rel-L2 {r:.4f} (autocast yardstick {y:.4f})" for n, r, y in report))
+    logit_rel = float(np.abs(logits - g["logits"]).max() / scale)
+    print(f"logits: max err / max|logit| {logit_rel:.4f} (autocast yardstick {float(g['yard_logits']):.4f})")
 
 
 @pytest.mark.parametrize("name", ["vilbert_tiny", "vilbert_tiny_ragged"])
