@@ -114,7 +114,17 @@ def _declare(l: C.CDLL) -> None:
         fn.restype = C.c_int
 
 
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of successful kernel-launching ABI calls made from this process (each is exactly one kernel launch)."""
+    return _launches
+
+
 def check(rc: int, what: str) -> None:
+    global _launches
+    _launches += 1
     if rc != 0:
         msg = lib().vb_last_error().decode("utf-8", "replace")
         raise VbError(f"{what} failed with status {rc}: {msg}")

@@ -190,6 +190,7 @@ class _FlatParams:
                     "bert.embeddings.token_type_embeddings.weight", "bert.embeddings.position_embeddings.weight",
                     "bert.embeddings.word_embeddings.weight"]
         used = set(order_w) | set(order_s)
+        self.order_w = order_w
         order_u = [k for k in named if k not in used]
         assert all("q_dense" in k for k in order_u), order_u
 
@@ -223,6 +224,17 @@ class _FlatParams:
             p.data = view
         self._ptrs = {k: p.data_ptr() for k, p in named.items()}
         self._version = -1
+        # gradient buckets for data-parallel training: one per encoder block, in flat-buffer order
+        from . import ddp
+        groups: Dict[str, List[str]] = {}
+        for k in order_w:
+            parts = k.split(".")
+            if parts[1] == "encoder":
+                name = {"layer": "t", "v_layer": "v", "c_layer": "c"}[parts[2]] + parts[3]
+            else:
+                name = "tail"
+            groups.setdefault(name, []).append(k)
+        self.buckets = ddp.block_ranges(self.offsets, {k: named[k].numel() for k in named}, list(groups.items()), self.s_end)
 
     # fused q|k|v biases are laid out back to back: check rather than assume
     def check_contiguous(self, keys: List[str]):
@@ -277,6 +289,8 @@ class _Plan:
         self.bwd_graph = None
         self.fwd_runs = 0
         self.bwd_runs = 0
+        self.fwd_launches = 0
+        self.bwd_launches = 0
         self.fwd_id = 0
         dev = eng.flat.device
         self.s_v = torch.cuda.Stream(device=dev)
@@ -316,7 +330,8 @@ class _Engine:
         self.use_graphs = os.environ.get("VB_NO_GRAPH", "0") != "1"
         self.two_streams = os.environ.get("VB_ONE_STREAM", "0") != "1"
         self.launches = 0
-        self.grad_hook = None      # data-parallel: called inside backward as hook(flat_grad_range_lo, hi)
+        self.comm_group = getattr(model, "_ddp_group", None)   # data-parallel: see ddp.attach()
+        self.comm_stream = torch.cuda.Stream(device=device) if self.comm_group is not None else None
         self._site = 0
         f = self.flat
         for p in [f"bert.encoder.layer.{i}.attention.self" for i in range(self.cfg["num_hidden_layers"])] + \
@@ -367,6 +382,18 @@ class _Engine:
                           dbias=f.g(bias_key) if bias_key else None,
                           p_in=p_in if drop else 0.0, site_in=site, p_out=p_out if drop else 0.0, site_out=site + 1,
                           seed=self.seed if drop else None)
+
+    def _bucket_ready(self, name, producers):
+        """Data-parallel: average one finished gradient bucket over the ranks, on the communication stream, as soon as
+        the producing stream(s) have written it (overlaps the rest of the backward pass)."""
+        if self.comm_group is None:
+            return
+        from . import ddp
+        lo, hi = self.flat.buckets[name]
+        for s in producers:
+            self.comm_stream.wait_stream(s)
+        with torch.cuda.stream(self.comm_stream):
+            ddp.all_reduce_mean(self.flat.grad[lo:hi], self.comm_group)
 
     def _next_site(self):
         self._site += 2
@@ -601,13 +628,16 @@ class _Engine:
                 c -= 1
                 self._co_layer_bwd(pl, c, sv[f"c{c}"], dy_v[iv_], dy_t[it_], dy_v[1 - iv_], dy_t[1 - it_], s_t, s_v)
                 iv_, it_ = 1 - iv_, 1 - it_
+                self._bucket_ready(f"c{c}", [s_t, s_v])
                 with torch.cuda.stream(s_v):
                     self._bert_layer_bwd(pl, f"bert.encoder.v_layer.{c}", sv[f"v{c}"], dy_v[iv_], dy_v[1 - iv_], Mv, R, Hv,
                                          nhv, Iv, pl.v_bias, pvh, pvh, "gv")
                 iv_ = 1 - iv_
+                self._bucket_ready(f"v{c}", [s_v])
             self._bert_layer_bwd(pl, f"bert.encoder.layer.{i}", sv[f"t{i}"], dy_t[it_], dy_t[1 - it_], Mt, T, H, nh, I,
                                  pl.t_bias, ph, ph, "gt")
             it_ = 1 - it_
+            self._bucket_ready(f"t{i}", [s_t])
 
         # embeddings
         with torch.cuda.stream(s_v):
@@ -628,6 +658,9 @@ class _Engine:
                            dbeta=f.g(e + ".LayerNorm.bias"), p_out=ph if pl.dropout else 0.0, site_out=sv["emb_site"],
                            seed=self.seed if pl.dropout else None)
         s_t.wait_stream(s_v)
+        self._bucket_ready("tail", [s_t])
+        if self.comm_stream is not None:
+            s_t.wait_stream(self.comm_stream)
 
     @staticmethod
     def _co_index(text_layer):
@@ -691,7 +724,9 @@ class _Engine:
         else:
             pl.bwd_runs += 1
         if not self.use_graphs or runs == 0:
+            lc = _lib.launch_count()
             fn(pl)  # eager (also the warm-up that loads modules / sets function attributes before any capture)
+            setattr(pl, which + "_launches", _lib.launch_count() - lc)
             return
         if graph is None:
             torch.cuda.synchronize()
@@ -738,8 +773,6 @@ class _Step(torch.autograd.Function):
         if any(p.grad is not None for _, p in params):
             carry = {k: p.grad.clone() for k, p in params if p.grad is not None}   # gradient accumulation (rare path)
         eng._execute(plan, "bwd")
-        if eng.grad_hook is not None:
-            eng.grad_hook()
         for k, p in params:
             g = flat.g(k)
             if carry is not None and k in carry:
@@ -763,6 +796,7 @@ class ViLBERTForClassification(nn.Module):
                                         nn.Dropout(0.1), nn.Linear(config["bi_hidden_size"], num_labels))
         self._engine: Optional[_Engine] = None
         self._anchor = None
+        self._ddp_group = None
         if config["bi_hidden_size"] != config["v_hidden_size"]:
             raise VbError("bi_hidden_size must equal v_hidden_size (as in the reference's v_pooler / BiOutput)")
 
