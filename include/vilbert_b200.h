@@ -193,6 +193,34 @@ typedef struct vb_attn_args {
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
 int vb_attention_bwd(const vb_attn_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ResNet-152 RoI feature stage (models/feature_extractors/resnet152_roi.py).  Activations are NHWC bf16; every
+ * convolution of torchvision's resnet152 (conv1..layer3 at :49-57 = forward_base, layer4 at :69-74 = forward_top) runs as
+ * vb_gemm_bf16 over [pixels, kh*kw*Cin] with the eval-mode BatchNorm folded into `scale` / `bias`, the bottleneck's
+ * identity as `aux` (VB_AUX_ADD) and VB_ACT_RELU.  The kernels below produce the GEMM operands and pool.
+ * ---------------------------------------------------------------------------------------------- */
+/* conv1 7x7/2 operand: fp32 NCHW image [n,3,h,w] -> bf16 [n*ho*wo, kpad], column (ky*kw+kx)*3+c, zero tail up to kpad */
+int vb_stem_im2col(const float* img, void* y, int32_t n, int32_t h, int32_t w, int32_t kh, int32_t kw, int32_t stride,
+                   int32_t pad, int32_t kpad, void* stream);
+/* bf16 NHWC [n,h,w,c] -> bf16 [n*ho*wo, kh*kw*c], column (ky*kw+kx)*c+ci (3x3 convolutions; 1x1 stride-2 downsample) */
+int vb_im2col_nhwc(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t kh, int32_t kw,
+                   int32_t stride, int32_t pad, void* stream);
+/* nn.MaxPool2d(k, stride, pad) on NHWC bf16 (resnet.maxpool, :52) */
+int vb_maxpool_nhwc(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, int32_t stride,
+                    int32_t pad, void* stream);
+/* torchvision.ops.RoIPool((ph,pw), spatial_scale) (:126, :167-170): rois fp32 [r,5] = (batch index, x1, y1, x2, y2);
+ * out bf16 [r,ph,pw,c]; argmax (optional) int32 [r,ph,pw,c] = iy*w+ix of the selected element, -1 for an empty bin.
+ * Index arithmetic is bit-exact with torchvision (round-half-away, floor/ceil bins, clipping, empty bin -> 0). */
+int vb_roi_pool_nhwc(const void* x, const float* rois, void* y, int32_t* argmax, int32_t num_rois, int32_t n, int32_t h,
+                     int32_t w, int32_t c, int32_t ph, int32_t pw, float spatial_scale, void* stream);
+/* torchvision.ops.roi_align(output_size, spatial_scale, sampling_ratio, aligned) as used by MultiScaleRoIAlign in
+ * models/feature_extractors/fasterrcnn_resnet152.py:130-134 (7x7, sampling_ratio 2) */
+int vb_roi_align_nhwc(const void* x, const float* rois, void* y, int32_t num_rois, int32_t n, int32_t h, int32_t w,
+                      int32_t c, int32_t ph, int32_t pw, float spatial_scale, int32_t sampling_ratio, int32_t aligned,
+                      void* stream);
+/* AdaptiveAvgPool2d((1,1)) + flatten (:71-73): bf16 [r, s, c] -> fp32 [r, c] */
+int vb_avgpool_nhwc(const void* x, float* out, int32_t r, int32_t s, int32_t c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

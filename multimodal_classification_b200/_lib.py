@@ -107,6 +107,12 @@ def _declare(l: C.CDLL) -> None:
         "vb_loc_embed_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],
         "vb_cls_ce_fwd": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "vb_cls_ce_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "vb_stem_im2col": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "vb_im2col_nhwc": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+        "vb_maxpool_nhwc": [vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+        "vb_roi_pool_nhwc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
+        "vb_roi_align_nhwc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, i32, i32, vp],
+        "vb_avgpool_nhwc": [vp, vp, i32, i32, i32, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)

@@ -96,6 +96,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// D[global] += smem tile (element type comes from the tensor map: fp32 here); split-K / accumulating outputs
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -201,6 +208,29 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+
+// Cheap erf-GELU for the GEMM epilogues: Phi(x) = 0.5 (1 + erf(x / sqrt 2)) ~= 0.5 + 0.5 tanh(x (a + b x^2 + c x^4)), a minimax fit
+// (max |x Phi - x Phi_fit| = 2.5e-5 over the reals, x^2 clamped at 36 where tanh has saturated) evaluated with the hardware
+// tanh (MUFU, rel. error 2^-11).  Both errors are an order of magnitude below the bf16 rounding of the stored result.
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float phi_tanh_arg(float x) {
+  const float u = fminf(x * x, 36.0f);
+  return x * fmaf(u, fmaf(u, -3.51902393e-4f, 3.70080200e-2f), 7.97505275e-1f);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_fast(phi_tanh_arg(x)), hx);
+}
+// d/dx [x Phi(x)] = Phi(x) + x phi(x), phi(x) = exp(-x^2/2) / sqrt(2 pi)
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  const float cdf = fmaf(0.5f, tanh_fast(phi_tanh_arg(x)), 0.5f);
+  const float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
+  return fmaf(x, pdf, cdf);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -15,62 +15,61 @@
 namespace vb {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;       // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_THREADS = 192; // 6 warps
+constexpr int GEMM_BK = 64;         // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_EPI_WARPS = 8;   // two per TMEM sub-partition, each takes half of a column panel
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_ACC_STAGES = 2;
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_BOX_BYTES = GEMM_BM * 128;  // one epilogue staging box: 128 rows x 128 bytes, 128B-swizzled
+constexpr int GEMM_SMEM_LIMIT = 227 * 1024;
 
 struct GemmKernelParams {
-  void* d;
-  void* d_preact;
   const float* scale;
   const float* bias;
-  const __nv_bfloat16* aux;
-  long long ldd, ld_preact, ld_aux;
   int m, n, k;
-  int d_is_f32, accumulate, act, aux_mode;
+  int d_is_f32, reduce_add, act, aux_mode, has_preact;
   int splits, kb_per_split;
   int m_tiles, n_tiles;
+  int stages;       // depth of the operand ring
+  int out_bytes;    // staging bytes for one column panel of the output
+  int x_bytes;      // staging bytes for the aux-in / preact-out panel (0 = unused)
 };
 
-template <int BN>
-struct GemmSmem {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 1024;
-  static constexpr int BUDGET = 200 * 1024;
-  static constexpr int STAGES = (BUDGET - BAR_BYTES) / STAGE_BYTES < 8 ? (BUDGET - BAR_BYTES) / STAGE_BYTES : 8;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*alignment slack*/;
-};
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case VB_ACT_GELU: return gelu_erf(v);
-    case VB_ACT_RELU: return fmaxf(v, 0.0f);
-    case VB_ACT_TANH: return tanhf(v);
-    default: return v;
-  }
-}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory"); }
 
+// Epilogue data flow: the accumulator is read from TMEM one 32-column chunk per thread-row, combined with bias / scale
+// (staged in smem), an optional aux panel (prefetched by TMA while the main loop of the tile is still running) and the
+// activation, written into 128B-swizzled staging boxes and shipped with TMA stores (or TMA reduce-adds for split-K /
+// accumulating fp32 outputs), so global traffic is fully coalesced and asynchronous.
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_x,
                  const GemmKernelParams p) {
-  using S = GemmSmem<BN>;
-  constexpr int STAGES = S::STAGES;
-  constexpr uint32_t TMEM_COLS = GEMM_ACC_STAGES * BN;  // 128, 256 or 512: all powers of two >= 32
+  constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  constexpr int B_BYTES = BN * GEMM_BK * 2;
+  constexpr int PN = BN < 128 ? BN : 128;                // epilogue column panel
+  constexpr int PANELS = BN / PN;
+  constexpr uint32_t TMEM_COLS = GEMM_ACC_STAGES * BN;   // 128, 256 or 512: all powers of two >= 32
   constexpr uint32_t IDESC = umma_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.stages;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * S::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint8_t* smem_b = smem_a + STAGES * A_BYTES;
+  uint8_t* stage_out = smem_b + STAGES * B_BYTES;
+  uint8_t* stage_x = stage_out + p.out_bytes;
+  float* s_bias = reinterpret_cast<float*>(stage_x + p.x_bytes);
+  float* s_scale = s_bias + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_scale + BN);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;
-  uint64_t* tmem_empty_bar = bars + 2 * STAGES + GEMM_ACC_STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * GEMM_ACC_STAGES);
+  uint64_t* empty_bar = bars + GEMM_MAX_STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * GEMM_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + GEMM_ACC_STAGES;
+  uint64_t* aux_full_bar = tmem_empty_bar + GEMM_ACC_STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(aux_full_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -78,14 +77,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_d);
+    if (p.x_bytes) tma_prefetch_desc(&tma_x);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < GEMM_ACC_STAGES; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
+    mbar_init(aux_full_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -98,7 +100,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint32_t tmem_base = *tmem_base_slot;
 
   const int total_kb = (p.k + GEMM_BK - 1) / GEMM_BK;
-  const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int mn_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = mn_tiles * p.splits;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -106,17 +109,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mn = tile % (p.m_tiles * p.n_tiles);
-        const int split = tile / (p.m_tiles * p.n_tiles);
+        const int mn = tile % mn_tiles;
+        const int split = tile / mn_tiles;
         const int m0 = (mn % p.m_tiles) * GEMM_BM;
         const int n0 = (mn / p.m_tiles) * BN;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-          uint8_t* sa = smem_a + stage * S::A_BYTES;
-          uint8_t* sb = smem_b + stage * S::B_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
+          uint8_t* sa = smem_a + stage * A_BYTES;
+          uint8_t* sb = smem_b + stage * B_BYTES;
           const int k0 = kb * GEMM_BK;
           if constexpr (A_MN) {
 #pragma unroll
@@ -141,7 +144,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int split = tile / (p.m_tiles * p.n_tiles);
+      const int split = tile / mn_tiles;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(total_kb, kb0 + p.kb_per_split);
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
@@ -151,8 +154,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem_a + stage * S::A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * S::B_BYTES);
+          const uint32_t sa = smem_u32(smem_a + stage * A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * B_BYTES);
 #pragma unroll
           for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
             uint64_t da, db;
@@ -172,124 +175,154 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       if (++acc == GEMM_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quarter = warp & 3;  // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int quarter = warp & 3;           // TMEM sub-partition this warp may read: lanes [32q, 32q+32)
+    const int half = (warp - 2) >> 2;       // which half of a column panel this warp converts
+    const int epi_tid = threadIdx.x - 64;
+    const bool leader = epi_tid == 0;
+    const int row = quarter * 32 + lane;    // row inside the tile
+    const uint32_t swz = static_cast<uint32_t>(row & 7);
+    const bool has_aux = p.aux_mode != VB_AUX_NONE;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mn = tile % (p.m_tiles * p.n_tiles);
+      const int mn = tile % mn_tiles;
       const int m0 = (mn % p.m_tiles) * GEMM_BM;
       const int n0 = (mn / p.m_tiles) * BN;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.m;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.n) {
+      for (int panel = 0; panel < PANELS; ++panel) {
+        const int pn0 = n0 + panel * PN;
+        if (leader) {
+          tma_store_wait_read();            // staging boxes of the previous panel have been read by the TMA engine
+          if (has_aux) {
+            mbar_arrive_expect_tx(aux_full_bar, GEMM_BM * PN * 2);
+#pragma unroll
+            for (int b = 0; b < (PN + 63) / 64; ++b)
+              tma_load_2d(stage_x + b * GEMM_BOX_BYTES, &tma_x, aux_full_bar, pn0 + b * 64, m0);
+          }
+        }
+        if (panel == 0) {
+          for (int i = epi_tid; i < BN; i += GEMM_EPI_WARPS * 32) {
+            const bool ok = n0 + i < p.n;
+            s_bias[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n0 + i) : 0.0f;
+            s_scale[i] = (p.scale != nullptr && ok) ? __ldg(p.scale + n0 + i) : 1.0f;
+          }
+        }
+        epi_barrier();                      // staging free, bias / scale visible
+        if (panel == 0) {
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          tc_fence_after();
+        }
+        if (has_aux) {
+          mbar_wait(aux_full_bar, aux_phase);
+          aux_phase ^= 1u;
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < PN / 64; ++cc) {
+          const int pcol = half * (PN / 2) + cc * 32;   // first of my 32 columns inside the panel
+          const int tcol = panel * PN + pcol;           // ... inside the tile
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + tcol, r);
+          tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          const int ncols = min(32, p.n - col0);  // multiple of 8 (host checks n % 8 == 0)
-          if (p.scale != nullptr) {
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s = *reinterpret_cast<const float4*>(s_scale + tcol + i);
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + tcol + i);
+            v[i] = fmaf(__uint_as_float(r[i]), s.x, b.x);
+            v[i + 1] = fmaf(__uint_as_float(r[i + 1]), s.y, b.y);
+            v[i + 2] = fmaf(__uint_as_float(r[i + 2]), s.z, b.z);
+            v[i + 3] = fmaf(__uint_as_float(r[i + 3]), s.w, b.w);
+          }
+          // bf16 panels: 64 columns per box, my 32 columns are 16-byte pieces [piece0, piece0+4) of box `xbox`
+          const int xbox = pcol >> 6;
+          const uint32_t piece0 = static_cast<uint32_t>((pcol & 63) >> 3);
+          uint8_t* xrow = stage_x + xbox * GEMM_BOX_BYTES + row * 128;
+          if (p.has_preact) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (i < ncols) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + col0 + i));
-                v[i] *= s.x; v[i + 1] *= s.y; v[i + 2] *= s.z; v[i + 3] *= s.w;
-              }
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(xrow + (((piece0 + j) ^ swz) << 4)) = o;
             }
           }
-          if (p.bias != nullptr) {
+          if (has_aux) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (i < ncols) {
-                const float4 s = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
-                v[i] += s.x; v[i + 1] += s.y; v[i + 2] += s.z; v[i + 3] += s.w;
-              }
-            }
-          }
-          if (p.d_preact != nullptr) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.d_preact) + static_cast<long long>(row) * p.ld_preact + col0;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 a = *reinterpret_cast<const uint4*>(xrow + (((piece0 + j) ^ swz) << 4));
+              const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+              const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+              if (p.aux_mode == VB_AUX_ADD) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i < ncols) {
-                uint4 o;
-                o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(dst + i) = o;
-              }
-            }
-          }
-          if (p.aux_mode != VB_AUX_NONE) {
-            const __nv_bfloat16* src = p.aux + static_cast<long long>(row) * p.ld_aux + col0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i < ncols) {
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + i));
-                const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-                const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-                if (p.aux_mode == VB_AUX_ADD) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[i + j] += av[j];
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[i + j] *= gelu_erf_grad(av[j]);
-                }
-              }
-            }
-          }
-          if (p.act != VB_ACT_NONE) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-          }
-          if (p.d_is_f32) {
-            float* dst = reinterpret_cast<float*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
-            if (p.accumulate) {
-              if (p.splits > 1) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (i < ncols) atomicAdd(dst + i, v[i]);
+                for (int i = 0; i < 8; ++i) v[8 * j + i] += av[i];
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  if (i < ncols) {
-                    float4 o = *reinterpret_cast<float4*>(dst + i);
-                    o.x += v[i]; o.y += v[i + 1]; o.z += v[i + 2]; o.w += v[i + 3];
-                    *reinterpret_cast<float4*>(dst + i) = o;
-                  }
-                }
+                for (int i = 0; i < 8; ++i) v[8 * j + i] *= gelu_fast_grad(av[i]);
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                if (i < ncols) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.d) + static_cast<long long>(row) * p.ldd + col0;
+          }
+          if (p.act == VB_ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (i < ncols) {
-                uint4 o;
-                o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(dst + i) = o;
-              }
+            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+          } else if (p.act == VB_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          } else if (p.act == VB_ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+          }
+          if (p.d_is_f32) {
+            // fp32 panels: 32 columns per box = exactly my chunk, eight 16-byte pieces
+            uint8_t* orow = stage_out + (pcol >> 5) * GEMM_BOX_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(orow + ((static_cast<uint32_t>(j) ^ swz) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint8_t* orow = stage_out + xbox * GEMM_BOX_BYTES + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * j], v[8 * j + 1]); o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]); o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(orow + (((piece0 + j) ^ swz) << 4)) = o;
             }
           }
         }
+        if (panel == PANELS - 1) {
+          // accumulator stage drained: hand it back to the MMA warp before the stores are even issued
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        fence_proxy_async_smem();           // make the staged panel visible to the TMA engine
+        epi_barrier();
+        if (leader && pn0 < p.n) {
+          if (p.d_is_f32) {
+#pragma unroll
+            for (int b = 0; b < PN / 32; ++b) {
+              if (pn0 + b * 32 < p.n) {
+                if (p.reduce_add) tma_reduce_add_2d(&tma_d, stage_out + b * GEMM_BOX_BYTES, pn0 + b * 32, m0);
+                else              tma_store_2d(&tma_d, stage_out + b * GEMM_BOX_BYTES, pn0 + b * 32, m0);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < (PN + 63) / 64; ++b) {
+              if (pn0 + b * 64 < p.n) {
+                tma_store_2d(&tma_d, stage_out + b * GEMM_BOX_BYTES, pn0 + b * 64, m0);
+                if (p.has_preact) tma_store_2d(&tma_x, stage_x + b * GEMM_BOX_BYTES, pn0 + b * 64, m0);
+              }
+            }
+          }
+          tma_store_commit();
+        }
       }
-      // accumulator stage drained: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == GEMM_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
+    if (leader) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -318,8 +351,9 @@ static int num_sms() {
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const vb_gemm_args& a, int splits, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
-  CUtensorMap map_a, map_b;
+  constexpr int PN = BN < 128 ? BN : 128;
+  constexpr int STAGE_BYTES = (GEMM_BM + BN) * GEMM_BK * 2;
+  CUtensorMap map_a, map_b, map_d, map_x;
   int rc;
   // K-major operand: global [rows, K] -> box {64 (k), rows_per_tile}; MN-major: global [K, rows] -> box {64 (mn), 64 (k)}
   if (A_MN) rc = make_tensor_map_2d(&map_a, a.a, /*inner*/ a.m, /*outer*/ a.k, a.lda, 64, GEMM_BK);
@@ -328,31 +362,55 @@ static int launch_gemm(const vb_gemm_args& a, int splits, cudaStream_t stream) {
   if (B_MN) rc = make_tensor_map_2d(&map_b, a.b, a.n, a.k, a.ldb, 64, GEMM_BK);
   else      rc = make_tensor_map_2d(&map_b, a.b, a.k, a.n, a.ldb, GEMM_BK, BN);
   if (rc != VB_OK) return rc;
+  // epilogue boxes: 128 rows x 128 bytes (64 bf16 or 32 fp32 columns)
+  if (a.d_is_f32) rc = make_tensor_map_2d_f32(&map_d, a.d, a.n, a.m, a.ldd, 32, GEMM_BM);
+  else            rc = make_tensor_map_2d(&map_d, a.d, a.n, a.m, a.ldd, PN < 64 ? PN : 64, GEMM_BM);
+  if (rc != VB_OK) return rc;
+  const void* xptr = a.d_preact != nullptr ? a.d_preact : a.aux;
+  const int64_t ldx = a.d_preact != nullptr ? a.ld_preact : a.ld_aux;
+  if (xptr != nullptr) {
+    rc = make_tensor_map_2d(&map_x, xptr, a.n, a.m, ldx, PN < 64 ? PN : 64, GEMM_BM);
+    if (rc != VB_OK) return rc;
+  } else {
+    map_x = map_d;
+  }
 
   GemmKernelParams p;
-  p.d = a.d; p.d_preact = a.d_preact; p.scale = a.scale; p.bias = a.bias;
-  p.aux = reinterpret_cast<const __nv_bfloat16*>(a.aux);
-  p.ldd = a.ldd; p.ld_preact = a.ld_preact; p.ld_aux = a.ld_aux;
+  p.scale = a.scale; p.bias = a.bias;
   p.m = a.m; p.n = a.n; p.k = a.k;
-  p.d_is_f32 = a.d_is_f32; p.accumulate = a.accumulate; p.act = a.act; p.aux_mode = a.aux_mode;
+  p.d_is_f32 = a.d_is_f32; p.act = a.act; p.aux_mode = a.aux_mode;
+  p.has_preact = a.d_preact != nullptr;
   p.m_tiles = (a.m + GEMM_BM - 1) / GEMM_BM;
   p.n_tiles = (a.n + BN - 1) / BN;
   const int total_kb = (a.k + GEMM_BK - 1) / GEMM_BK;
   if (splits > total_kb) splits = total_kb;
   p.kb_per_split = (total_kb + splits - 1) / splits;
   p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty split
+  p.reduce_add = (a.accumulate || p.splits > 1) ? 1 : 0;
+  p.out_bytes = GEMM_BM * PN * (a.d_is_f32 ? 4 : 2);
+  if (p.out_bytes < GEMM_BOX_BYTES) p.out_bytes = GEMM_BOX_BYTES;
+  p.x_bytes = xptr != nullptr ? (GEMM_BM * PN * 2 < GEMM_BOX_BYTES ? GEMM_BOX_BYTES : GEMM_BM * PN * 2) : 0;
+  const int fixed = 1024 /*alignment slack*/ + p.out_bytes + p.x_bytes + 2 * BN * 4 + 256 /*barriers*/;
+  int stages = (GEMM_SMEM_LIMIT - fixed) / STAGE_BYTES;
+  if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+  if (stages < 2) {
+    vb_set_last_error("vb_gemm_bf16", "tile configuration does not fit shared memory");
+    return VB_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  const int smem_bytes = fixed + stages * STAGE_BYTES;
 
-  static bool attr_set = false;
+  static int attr_bytes = 0;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
-  if (!attr_set) {
-    VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
+  if (attr_bytes < smem_bytes) {
+    VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_LIMIT));
+    attr_bytes = GEMM_SMEM_LIMIT;
   }
   const int tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = num_sms();
   if (a.max_ctas > 0 && a.max_ctas < grid) grid = a.max_ctas;
   if (tiles < grid) grid = tiles;
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(map_a, map_b, p);
+  kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(map_a, map_b, map_d, map_x, p);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;
 }
@@ -419,6 +477,8 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* args, void* stream) {
   VB_REQUIRE(a.splits >= 0 && (a.splits <= 1 || (a.d_is_f32 && a.accumulate)), "split-K needs an fp32 accumulating output");
   VB_REQUIRE(!(a.accumulate && !a.d_is_f32), "accumulate needs an fp32 output");
   VB_REQUIRE(!(a.d_is_f32 && a.d_preact != nullptr), "d_preact only with a bf16 output");
+  VB_REQUIRE(!(a.d_preact != nullptr && a.aux_mode != VB_AUX_NONE), "d_preact and aux share one staging panel: use one of them");
+  VB_REQUIRE(!(a.d_is_f32 && a.aux_mode != VB_AUX_NONE), "aux only with a bf16 output");
   int bn = 128, splits = 1;
   pick_config(a, &bn, &splits);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

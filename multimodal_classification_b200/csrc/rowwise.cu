@@ -117,58 +117,76 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
   }
 }
 
-// block-level accumulation of per-lane column partials into global fp32 (atomics; the destination is zeroed by the
-// caller at the start of every backward pass)
+// Column partials (dgamma / dbeta / dbias): every warp parks its per-lane sums in its own smem row (plain stores), the
+// block adds the LN_WARPS rows per column and issues ONE global atomicAdd per column (destination zeroed by the caller
+// at the start of every backward pass).
 template <int NV>
-__device__ __forceinline__ void flush_colsum(float (&acc)[NV][8], float* smem, float* gdst, int h, int lane) {
-  __syncthreads();
-  for (int i = threadIdx.x; i < h; i += blockDim.x) smem[i] = 0.f;
-  __syncthreads();
+__device__ __forceinline__ void flush_colsum(const float (&acc)[NV][8], float* smem, float* gdst, int h, int lane, int warp) {
+  __syncthreads();   // previous use of `smem` is over
 #pragma unroll
-  for (int j = 0; j < NV; ++j)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(&smem[(lane + 32 * j) * 8 + i], acc[j][i]);
+  for (int j = 0; j < NV; ++j) {
+    float* dst = smem + warp * h + (lane + 32 * j) * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < h; i += blockDim.x) atomicAdd(&gdst[i], smem[i]);
+  for (int c = threadIdx.x; c < h; c += blockDim.x) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) sum += smem[w * h + c];
+    atomicAdd(&gdst[c], sum);
+  }
 }
 
 template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnParams p) {
-  extern __shared__ float ln_smem[];
+  extern __shared__ float ln_smem[];   // [LN_WARPS][h]
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint64_t seed = p.seed ? *p.seed : 0ull;
   const bool drop_in = p.p_in > 0.f && p.seed, drop_out = p.p_out > 0.f && p.seed;
   const uint32_t thr_in = dropout_threshold(p.p_in), thr_out = dropout_threshold(p.p_out);
   const float inv_in = drop_in ? 1.f / (1.f - p.p_in) : 1.f, inv_out = drop_out ? 1.f / (1.f - p.p_out) : 1.f;
+  const float inv_h = 1.0f / (float)p.h;
   float dg[NV][8], db[NV][8], dbx[NV][8];
 #pragma unroll
   for (int j = 0; j < NV; ++j)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dg[j][i] = 0.f; db[j][i] = 0.f; dbx[j][i] = 0.f; }
   for (int row = blockIdx.x * LN_WARPS + warp; row < p.m; row += gridDim.x * LN_WARPS) {
+    // issue every global load of the row first (3 x NV independent 16-byte loads per lane)
+    uint4 xr[NV], rr[NV], dr[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int col = (lane + 32 * j) * 8;
+      xr[j] = *reinterpret_cast<const uint4*>(p.x + (long long)row * p.ldx + col);
+      dr[j] = *reinterpret_cast<const uint4*>(p.dy + (long long)row * p.lddy + col);
+      if (p.res) rr[j] = *reinterpret_cast<const uint4*>(p.res + (long long)row * p.ldres + col);
+    }
     const float mean = p.mean[row], rstd = p.rstd[row];
     float xh[NV][8], dxh[NV][8];
+    uint32_t keep_in[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int col = (lane + 32 * j) * 8;
-      float v[8];
-      ld8(p.x + (long long)row * p.ldx + col, v);
+      float v[8], d[8], g[8];
+      { const float2 a = unpack_bf16x2(xr[j].x), b = unpack_bf16x2(xr[j].y), c = unpack_bf16x2(xr[j].z), e = unpack_bf16x2(xr[j].w);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = e.x; v[7] = e.y; }
+      { const float2 a = unpack_bf16x2(dr[j].x), b = unpack_bf16x2(dr[j].y), c = unpack_bf16x2(dr[j].z), e = unpack_bf16x2(dr[j].w);
+        d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y; d[4] = c.x; d[5] = c.y; d[6] = e.x; d[7] = e.y; }
+      keep_in[j] = 0xFFu;
       if (drop_in) {
         bool k[8];
         keep8(seed, p.site_in, (uint32_t)row * (uint32_t)p.h + col, thr_in, k);
+        keep_in[j] = 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = k[i] ? v[i] * inv_in : 0.f;
+        for (int i = 0; i < 8; ++i) { v[i] = k[i] ? v[i] * inv_in : 0.f; keep_in[j] |= (k[i] ? 1u : 0u) << i; }
       }
       if (p.res) {
-        float r[8];
-        ld8(p.res + (long long)row * p.ldres + col, r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += r[i];
+        const float2 a = unpack_bf16x2(rr[j].x), b = unpack_bf16x2(rr[j].y), c = unpack_bf16x2(rr[j].z), e = unpack_bf16x2(rr[j].w);
+        v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += e.x; v[7] += e.y;
       }
-      float d[8], g[8];
-      ld8(p.dy + (long long)row * p.lddy + col, d);
       ld8f(p.gamma + col, g);
       if (drop_out) {
         bool k[8];
@@ -186,7 +204,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnParams p)
         s2 += dxh[j][i] * xh[j][i];
       }
     }
-    const float c1 = warp_sum(s1) / (float)p.h, c2 = warp_sum(s2) / (float)p.h;
+    const float c1 = warp_sum(s1) * inv_h, c2 = warp_sum(s2) * inv_h;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int col = (lane + 32 * j) * 8;
@@ -195,19 +213,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnParams p)
       for (int i = 0; i < 8; ++i) ds[i] = rstd * (dxh[j][i] - c1 - xh[j][i] * c2);
       if (p.dres) st8(p.dres + (long long)row * p.lddres + col, ds);
       if (drop_in) {
-        bool k[8];
-        keep8(seed, p.site_in, (uint32_t)row * (uint32_t)p.h + col, thr_in, k);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ds[i] = k[i] ? ds[i] * inv_in : 0.f;
+        for (int i = 0; i < 8; ++i) ds[i] = ((keep_in[j] >> i) & 1u) ? ds[i] * inv_in : 0.f;
       }
       if (p.dx) st8(p.dx + (long long)row * p.lddx + col, ds);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dbx[j][i] += ds[i];
     }
   }
-  if (p.dgamma) flush_colsum<NV>(dg, ln_smem, p.dgamma, p.h, lane);
-  if (p.dbeta) flush_colsum<NV>(db, ln_smem, p.dbeta, p.h, lane);
-  if (p.dbias) flush_colsum<NV>(dbx, ln_smem, p.dbias, p.h, lane);
+  if (p.dgamma) flush_colsum<NV>(dg, ln_smem, p.dgamma, p.h, lane, warp);
+  if (p.dbeta) flush_colsum<NV>(db, ln_smem, p.dbeta, p.h, lane, warp);
+  if (p.dbias) flush_colsum<NV>(dbx, ln_smem, p.dbias, p.h, lane, warp);
 }
 
 static int ln_grid(int m, int rows_per_warp) {
@@ -362,12 +378,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) emb_bwd_kernel(const EmbParams 
       }
     }
   }
-  if (p.dgamma) flush_colsum<NV>(dg, ln_smem, p.dgamma, p.h, lane);
-  if (p.dbeta) flush_colsum<NV>(db, ln_smem, p.dbeta, p.h, lane);
-  if (p.dpos) flush_colsum<NV>(dp, ln_smem, p.dpos + (long long)pos * p.h, p.h, lane);
+  if (p.dgamma) flush_colsum<NV>(dg, ln_smem, p.dgamma, p.h, lane, warp);
+  if (p.dbeta) flush_colsum<NV>(db, ln_smem, p.dbeta, p.h, lane, warp);
+  if (p.dpos) flush_colsum<NV>(dp, ln_smem, p.dpos + (long long)pos * p.h, p.h, lane, warp);
   if (p.dtype) {
-    flush_colsum<NV>(dt0, ln_smem, p.dtype, p.h, lane);
-    flush_colsum<NV>(dt1, ln_smem, p.dtype + p.h, p.h, lane);
+    flush_colsum<NV>(dt0, ln_smem, p.dtype, p.h, lane, warp);
+    flush_colsum<NV>(dt1, ln_smem, p.dtype + p.h, p.h, lane, warp);
   }
 }
 
@@ -628,7 +644,17 @@ extern "C" int vb_layernorm_bwd(const vb_layernorm_args* a, void* stream) {
   VB_REQUIRE(a->dy && (a->dx || a->dres), "dy and at least one of dx / dres are required");
   cudaStream_t s = (cudaStream_t)stream;
   rc = dispatch_nv(p.h, [&](auto nv) {
-    ln_bwd_kernel<decltype(nv)::value><<<ln_grid(p.m, 4), LN_WARPS * 32, p.h * sizeof(float), s>>>(p);
+    auto kern = ln_bwd_kernel<decltype(nv)::value>;
+    const int smem = LN_WARPS * p.h * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_WARPS * 2048 * (int)sizeof(float));
+      attr_set = true;
+    }
+    // one row per warp up to two full waves of blocks, then rows are strided over the grid
+    int grid = ln_grid(p.m, 1);
+    if (grid > 2 * 148) grid = ln_grid(p.m, (p.m + 2 * 148 * LN_WARPS - 1) / (2 * 148 * LN_WARPS));
+    kern<<<grid, LN_WARPS * 32, smem, s>>>(p);
     return VB_OK;
   });
   if (rc != VB_OK) return rc;
@@ -672,7 +698,7 @@ extern "C" int vb_embed_text_bwd(const vb_embed_args* a, void* stream) {
   VB_REQUIRE(a->dy, "dy is required");
   cudaStream_t s = (cudaStream_t)stream;
   rc = dispatch_nv(p.h, [&](auto nv) {
-    emb_bwd_kernel<decltype(nv)::value><<<p.t, LN_WARPS * 32, p.h * sizeof(float), s>>>(p);
+    emb_bwd_kernel<decltype(nv)::value><<<p.t, LN_WARPS * 32, LN_WARPS * p.h * sizeof(float), s>>>(p);
     return VB_OK;
   });
   if (rc != VB_OK) return rc;

@@ -293,7 +293,13 @@ class _Plan:
         self.bwd_launches = 0
         self.fwd_id = 0
         dev = eng.flat.device
-        self.s_v = torch.cuda.Stream(device=dev)
+        # chain streams (text = s_main, visual = s_v) run the forward and the dgrad chain at high priority; the weight
+        # gradients (off the critical path) go to low-priority side streams and fill the SMs the chain leaves idle
+        self.s_main = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_v = torch.cuda.Stream(device=dev, priority=-1)
+        self.s_tw = torch.cuda.Stream(device=dev)
+        self.s_vw = torch.cuda.Stream(device=dev)
+        self.side_events: Dict[str, torch.cuda.Event] = {}
         cfg = eng.cfg
         B, T, R = self.B, self.T, self.R
         self.Mt, self.Mv = B * T, B * R
@@ -329,6 +335,8 @@ class _Engine:
         self.seed = torch.tensor([int(os.environ.get("VB_SEED", "20260101"))], dtype=torch.int64, device=device)
         self.use_graphs = os.environ.get("VB_NO_GRAPH", "0") != "1"
         self.two_streams = os.environ.get("VB_ONE_STREAM", "0") != "1"
+        self.side_streams = self.two_streams and os.environ.get("VB_NO_SIDE", "0") != "1"
+        self._pl = None
         self.launches = 0
         self.comm_group = getattr(model, "_ddp_group", None)   # data-parallel: see ddp.attach()
         self.comm_stream = torch.cuda.Stream(device=device) if self.comm_group is not None else None
@@ -356,12 +364,37 @@ class _Engine:
         kernel that made dy, dx = dy W (+ aux | * gelu'(aux))."""
         f = self.flat
         w = f.w(wkey, rows)
-        ops.gemm(dy, x, f.g(wkey, shape=tuple(w.shape), numel=w.numel()), a_mn_major=True, b_mn_major=True)
-        if bias_grad:
-            bkey = wkey[:-len("weight")] + "bias"
-            ops.colsum(dy, f.g(bkey, numel=w.shape[0]))
+        cur = torch.cuda.current_stream()
+        side = self._side_stream(cur)
+        if side is not None:
+            side.wait_stream(cur)     # dy is complete on the chain stream
+        with torch.cuda.stream(side if side is not None else cur):
+            ops.gemm(dy, x, f.g(wkey, shape=tuple(w.shape), numel=w.numel()), a_mn_major=True, b_mn_major=True)
+            if bias_grad:
+                bkey = wkey[:-len("weight")] + "bias"
+                ops.colsum(dy, f.g(bkey, numel=w.shape[0]))
         if dx is not None:
             ops.gemm(dy, w, dx, b_mn_major=True, aux=aux, aux_mode=aux_mode)
+
+    def _side_stream(self, cur):
+        pl = self._pl
+        if pl is None or not self.side_streams:
+            return None
+        return pl.s_vw if cur == pl.s_v else pl.s_tw
+
+    def _scratch_begin(self, pl, prefix):
+        """The chain is about to overwrite scratch buffers `prefix.*`: wait for the weight-gradient GEMMs that read their
+        previous contents (recorded by _scratch_end two layers ago: scratch is double-buffered by layer parity)."""
+        ev = pl.side_events.get(prefix)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _scratch_end(self, pl, prefix):
+        side = self._side_stream(torch.cuda.current_stream())
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            pl.side_events[prefix] = ev
 
     def _ln(self, pl, x, res, lnkey, y, tag, p_in=0.0, p_out=0.0):
         f = self.flat
@@ -437,6 +470,7 @@ class _Engine:
         return g_a
 
     def _bert_layer_bwd(self, pl, p, sv, dy, dx_out, M, S, H, heads, inter, bias, p_hidden, p_attn, sc):
+        self._scratch_begin(pl, sc)
         g_a = self._ffn_bwd(pl, p + ".intermediate.dense", p + ".output.dense", p + ".output.LayerNorm", sv["ln2"], dy,
                             sv["fo"], sv["a"], sv["pre"], sv["it"], M, H, inter, sc, p_hidden)
         g_ao = pl.buf(sc + ".g_ao", (M, H))
@@ -452,11 +486,13 @@ class _Engine:
                           p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"], seed=self.seed if pl.dropout else None)
         self._linear_bwd(g_qkv, sv["x"], p + ".attention.self.query.weight", rows=3 * H, dx=dx_out,
                          aux=g_xres if g_xres is not None else g_ao, aux_mode=ops.AUX_ADD)
+        self._scratch_end(pl, sc)
 
     # ------------------------------------------------------------------------------------------------ forward
     def run_forward(self, pl: _Plan):
         cfg, f = self.cfg, self.flat
         self._site = 0
+        self._pl = pl
         H, Hv, bi = cfg["hidden_size"], cfg["v_hidden_size"], cfg["bi_hidden_size"]
         I, Iv = cfg["intermediate_size"], cfg["v_intermediate_size"]
         nh, nhv = cfg["num_attention_heads"], cfg["v_num_attention_heads"]
@@ -589,8 +625,12 @@ class _Engine:
         ph, pa, pvh = cfg["hidden_dropout_prob"], cfg["attention_probs_dropout_prob"], cfg["v_hidden_dropout_prob"]
         B, T, R, Mt, Mv = pl.B, pl.T, pl.R, pl.Mt, pl.Mv
         sv = pl.saved
+        self._pl = pl
+        pl.side_events.clear()
         s_t = torch.cuda.current_stream()
         s_v = pl.s_v if self.two_streams else s_t
+        sides_t = [pl.s_tw] if self.side_streams else []
+        sides_v = [pl.s_vw] if self.side_streams else []
         # gradients that are accumulated with atomics start from zero (biases, LayerNorm, location weights, tables)
         f.grad[f.w_end:f.s_end].zero_()
         dy_t = [pl.buf("g.t_ping", (Mt, H)), pl.buf("g.t_pong", (Mt, H))]
@@ -628,16 +668,16 @@ class _Engine:
                 c -= 1
                 self._co_layer_bwd(pl, c, sv[f"c{c}"], dy_v[iv_], dy_t[it_], dy_v[1 - iv_], dy_t[1 - it_], s_t, s_v)
                 iv_, it_ = 1 - iv_, 1 - it_
-                self._bucket_ready(f"c{c}", [s_t, s_v])
+                self._bucket_ready(f"c{c}", [s_t, s_v] + sides_t + sides_v)
                 with torch.cuda.stream(s_v):
                     self._bert_layer_bwd(pl, f"bert.encoder.v_layer.{c}", sv[f"v{c}"], dy_v[iv_], dy_v[1 - iv_], Mv, R, Hv,
-                                         nhv, Iv, pl.v_bias, pvh, pvh, "gv")
+                                         nhv, Iv, pl.v_bias, pvh, pvh, f"gv{c & 1}")
                 iv_ = 1 - iv_
-                self._bucket_ready(f"v{c}", [s_v])
+                self._bucket_ready(f"v{c}", [s_v] + sides_v)
             self._bert_layer_bwd(pl, f"bert.encoder.layer.{i}", sv[f"t{i}"], dy_t[it_], dy_t[1 - it_], Mt, T, H, nh, I,
-                                 pl.t_bias, ph, ph, "gt")
+                                 pl.t_bias, ph, ph, f"gt{i & 1}")
             it_ = 1 - it_
-            self._bucket_ready(f"t{i}", [s_t])
+            self._bucket_ready(f"t{i}", [s_t] + sides_t)
 
         # embeddings
         with torch.cuda.stream(s_v):
@@ -658,6 +698,8 @@ class _Engine:
                            dbeta=f.g(e + ".LayerNorm.bias"), p_out=ph if pl.dropout else 0.0, site_out=sv["emb_site"],
                            seed=self.seed if pl.dropout else None)
         s_t.wait_stream(s_v)
+        for side in sides_t + sides_v:
+            s_t.wait_stream(side)
         self._bucket_ready("tail", [s_t])
         if self.comm_stream is not None:
             s_t.wait_stream(self.comm_stream)
@@ -677,26 +719,32 @@ class _Engine:
         p = f"bert.encoder.c_layer.{c}"
         drop = pl.dropout
         seed = self.seed if drop else None
-        g_tqkv = pl.buf(f"gc{c & 1}.tqkv", (Mt, 3 * bi))  # double-buffered: written from both streams
-        g_vqkv = pl.buf(f"gc{c & 1}.vqkv", (Mv, 3 * bi))
+        sct, scv = f"gct{c & 1}", f"gcv{c & 1}"              # scratch double-buffered by layer parity
+        self._scratch_begin(pl, sct)                         # both chains write both qkv-gradient buffers
+        self._scratch_begin(pl, scv)
+        with torch.cuda.stream(s_v):
+            self._scratch_begin(pl, sct)
+            self._scratch_begin(pl, scv)
+        g_tqkv = pl.buf(sct + ".tqkv", (Mt, 3 * bi))
+        g_vqkv = pl.buf(scv + ".vqkv", (Mv, 3 * bi))
         tqkv, vqkv = sv["tqkv"], sv["vqkv"]
         # text half down to the gradient of t_ctx
         g_tatt = self._ffn_bwd(pl, p + ".t_intermediate.dense", p + ".t_output.dense", p + ".t_output.LayerNorm", sv["t_ln2"],
-                               dt, sv["t_fo"], sv["t_att"], sv["t_pre"], sv["t_int"], Mt, H, I, "gct", ph)
-        g_tbo = pl.buf("gct.g_bo", (Mt, H))
-        g_tres = pl.buf("gct.g_res", (Mt, H)) if drop else None
+                               dt, sv["t_fo"], sv["t_att"], sv["t_pre"], sv["t_int"], Mt, H, I, sct, ph)
+        g_tbo = pl.buf(sct + ".g_bo", (Mt, H))
+        g_tres = pl.buf(sct + ".g_res", (Mt, H)) if drop else None
         self._ln_bwd(pl, g_tatt, sv["t_bo"], sv["t_in"], p + ".biOutput.LayerNorm2", sv["t_ln1"], dx=g_tbo, dres=g_tres,
                      bias_key=p + ".biOutput.dense2.bias", p_in=ph)
-        g_tctx = pl.buf("gct.g_ctx", (Mt, bi))
+        g_tctx = pl.buf(sct + ".g_ctx", (Mt, bi))
         self._linear_bwd(g_tbo, sv["t_ctx"], p + ".biOutput.dense2.weight", dx=g_tctx, bias_grad=False)
         with torch.cuda.stream(s_v):
             g_vatt = self._ffn_bwd(pl, p + ".v_intermediate.dense", p + ".v_output.dense", p + ".v_output.LayerNorm",
-                                   sv["v_ln2"], dv, sv["v_fo"], sv["v_att"], sv["v_pre"], sv["v_int"], Mv, Hv, Iv, "gcv", pvh)
-            g_vbo = pl.buf("gcv.g_bo", (Mv, Hv))
-            g_vres = pl.buf("gcv.g_res", (Mv, Hv)) if drop else None
+                                   sv["v_ln2"], dv, sv["v_fo"], sv["v_att"], sv["v_pre"], sv["v_int"], Mv, Hv, Iv, scv, pvh)
+            g_vbo = pl.buf(scv + ".g_bo", (Mv, Hv))
+            g_vres = pl.buf(scv + ".g_res", (Mv, Hv)) if drop else None
             self._ln_bwd(pl, g_vatt, sv["v_bo"], sv["v_in"], p + ".biOutput.LayerNorm1", sv["v_ln1"], dx=g_vbo, dres=g_vres,
                          bias_key=p + ".biOutput.dense1.bias", p_in=ph)
-            g_vctx = pl.buf("gcv.g_ctx", (Mv, bi))
+            g_vctx = pl.buf(scv + ".g_ctx", (Mv, bi))
             self._linear_bwd(g_vbo, sv["v_ctx"], p + ".biOutput.dense1.weight", dx=g_vctx, bias_grad=False)
             # regions attend to tokens: dq -> visual q1, dk/dv -> text k2/v2
             ops.attention_bwd(g_vctx, vqkv[:, :bi], tqkv[:, bi:2 * bi], tqkv[:, 2 * bi:], sv["v_lse"], g_vqkv[:, :bi],
@@ -710,9 +758,11 @@ class _Engine:
         s_v.wait_stream(s_t)
         self._linear_bwd(g_tqkv, sv["t_in"], p + ".biattention.query2.weight", rows=3 * bi, dx=dt_out,
                          aux=g_tres if g_tres is not None else g_tbo, aux_mode=ops.AUX_ADD)
+        self._scratch_end(pl, sct)
         with torch.cuda.stream(s_v):
             self._linear_bwd(g_vqkv, sv["v_in"], p + ".biattention.query1.weight", rows=3 * bi, dx=dv_out,
                              aux=g_vres if g_vres is not None else g_vbo, aux_mode=ops.AUX_ADD)
+            self._scratch_end(pl, scv)
 
     # ------------------------------------------------------------------------------------------------ execution
     def _execute(self, pl: _Plan, which: str):
@@ -723,21 +773,27 @@ class _Engine:
             pl.fwd_runs += 1
         else:
             pl.bwd_runs += 1
+        caller = torch.cuda.current_stream()
+        pl.s_main.wait_stream(caller)
         if not self.use_graphs or runs == 0:
             lc = _lib.launch_count()
-            fn(pl)  # eager (also the warm-up that loads modules / sets function attributes before any capture)
+            with torch.cuda.stream(pl.s_main):
+                fn(pl)  # eager (also the warm-up that loads modules / sets function attributes before any capture)
             setattr(pl, which + "_launches", _lib.launch_count() - lc)
+            caller.wait_stream(pl.s_main)
             return
         if graph is None:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            with torch.cuda.graph(graph, stream=pl.s_main, capture_error_mode="thread_local"):
                 fn(pl)
             if which == "fwd":
                 pl.fwd_graph = graph
             else:
                 pl.bwd_graph = graph
-        graph.replay()
+        with torch.cuda.stream(pl.s_main):
+            graph.replay()
+        caller.wait_stream(pl.s_main)
 
 
 class _Step(torch.autograd.Function):
