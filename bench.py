@@ -255,7 +255,7 @@ def main():
     launches_direct = _lib.launch_count() - lc0
     eng = model._engine
     plan = next(iter(eng.plans.values()))
-    launches = launches_direct + args.steps * (plan.fwd_launches + plan.bwd_launches)
+    launches = launches_direct // max(1, args.steps) + plan.fwd_launches + plan.bwd_launches   # kernels per step
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -285,7 +285,7 @@ def main():
                            "cuda_graphs": eng.use_graphs},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+                "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "roofline": roofline, "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, n = time_cpu_port(25.0, B)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -83,13 +83,7 @@ __device__ __forceinline__ void attn_keep_bits(uint64_t seed, uint32_t site, uin
   for (int w = 0; w < 4; ++w) {
     uint32_t m = 0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const uint4 r = dropout_bits(seed, site, row_index * 32u + w * 8 + q);
-      m |= (r.x >= thr ? 1u : 0u) << (q * 4 + 0);
-      m |= (r.y >= thr ? 1u : 0u) << (q * 4 + 1);
-      m |= (r.z >= thr ? 1u : 0u) << (q * 4 + 2);
-      m |= (r.w >= thr ? 1u : 0u) << (q * 4 + 3);
-    }
+    for (int q = 0; q < 4; ++q) m |= dropout_keep8(seed, site, row_index * 16u + w * 4 + q, thr) << (q * 8);
     keep[w] = m;
   }
 }

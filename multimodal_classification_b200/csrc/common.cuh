@@ -134,6 +134,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-collective forms: the WHOLE (converged) warp executes the call with warp-uniform operands and one elected lane
+// issues.  Unlike `if (lane == 0) umma_bf16(...)`, the call site is not divergent, so ptxas keeps the operands in uniform
+// registers and emits a straight UTCHMMA instead of an ELECT / R2UR / BRA.U.ANY loop around every instruction.
+__device__ __forceinline__ void umma_bf16_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -273,16 +293,28 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// keep-mask bits for elements [4*quad, 4*quad+4) of dropout site `site`
-__device__ __forceinline__ uint4 dropout_bits(uint64_t seed, uint32_t site, uint32_t quad) {
-  return philox4x32(quad, site, 0x5EEDu, 0u, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+// 128 random bits = eight 16-bit keep decisions: elements [8*oct, 8*oct+8) of dropout site `site`; element j uses the
+// low (j even) / high (j odd) half of word j/2.  16 bits per decision halve the Philox work; p is realised as
+// round(p * 65536) / 65536 (0.1 -> 0.100006).
+__device__ __forceinline__ uint4 dropout_bits(uint64_t seed, uint32_t site, uint32_t oct) {
+  return philox4x32(oct, site, 0x5EEDu, 0u, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
 }
-// threshold such that P(bits >= thr) = 1 - p  (keep)
+// 16-bit threshold such that P(bits16 >= thr) = 1 - p  (keep)
 __host__ __device__ inline uint32_t dropout_threshold(float p) {
-  double t = static_cast<double>(p) * 4294967296.0;
+  double t = static_cast<double>(p) * 65536.0 + 0.5;
   if (t < 0.0) t = 0.0;
-  if (t > 4294967295.0) t = 4294967295.0;
+  if (t > 65535.0) t = 65535.0;
   return static_cast<uint32_t>(t);
+}
+// bit j of the result = keep decision of element 8*oct + j
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t site, uint32_t oct, uint32_t thr) {
+  const uint4 r = dropout_bits(seed, site, oct);
+  uint32_t m = 0;
+  m |= ((r.x & 0xFFFFu) >= thr ? 1u : 0u) << 0; m |= ((r.x >> 16) >= thr ? 1u : 0u) << 1;
+  m |= ((r.y & 0xFFFFu) >= thr ? 1u : 0u) << 2; m |= ((r.y >> 16) >= thr ? 1u : 0u) << 3;
+  m |= ((r.z & 0xFFFFu) >= thr ? 1u : 0u) << 4; m |= ((r.z >> 16) >= thr ? 1u : 0u) << 5;
+  m |= ((r.w & 0xFFFFu) >= thr ? 1u : 0u) << 6; m |= ((r.w >> 16) >= thr ? 1u : 0u) << 7;
+  return m;
 }
 
 }  // namespace vb

@@ -8,6 +8,8 @@
 // Operands may be K-major or MN-major (descriptor + TMA box change only), so forward, dgrad and
 // wgrad of nn.Linear (reference models/vilbert_facebook_arch.py:127-129 etc.) all run here without a
 // transposed copy of anything.  See include/vilbert_b200.h for the ABI.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/vilbert_b200.h"
 #include "tensormap.h"
@@ -33,6 +35,7 @@ struct GemmKernelParams {
   int stages;       // depth of the operand ring
   int out_bytes;    // staging bytes for one column panel of the output
   int x_bytes;      // staging bytes for the aux-in / preact-out panel (0 = unused)
+  int debug_mode;   // profiling only (VB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads; results are garbage
 };
 
 
@@ -117,6 +120,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (p.debug_mode == 2 || p.debug_mode == 4) {
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           uint8_t* sa = smem_a + stage * A_BYTES;
           uint8_t* sb = smem_b + stage * B_BYTES;
@@ -153,24 +161,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem_a + stage * A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * B_BYTES);
+        if (p.debug_mode == 1) {
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        } else {
+          // descriptors differ from the stage base only in the 14-bit start-address field: +32 B per K step inside a
+          // K-major swizzle row, +2048 B (16 k-rows) per K step of an MN-major tile
+          const uint64_t da0 = A_MN ? umma_smem_desc(smem_u32(smem_a + stage * A_BYTES), GEMM_BK * 128, 1024)
+                                    : umma_smem_desc(smem_u32(smem_a + stage * A_BYTES), 16, 1024);
+          const uint64_t db0 = B_MN ? umma_smem_desc(smem_u32(smem_b + stage * B_BYTES), GEMM_BK * 128, 1024)
+                                    : umma_smem_desc(smem_u32(smem_b + stage * B_BYTES), 16, 1024);
 #pragma unroll
-          for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
-            uint64_t da, db;
-            if constexpr (A_MN) da = umma_smem_desc(sa + kk * 2048, GEMM_BK * 128, 1024);
-            else                da = umma_smem_desc(sa + kk * 32, 16, 1024);
-            if constexpr (B_MN) db = umma_smem_desc(sb + kk * 2048, GEMM_BK * 128, 1024);
-            else                db = umma_smem_desc(sb + kk * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, IDESC, (kb > kb0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          for (int kk = 0; kk < GEMM_BK / 16; ++kk)
+            umma_bf16_warp(tmem_d + ((p.debug_mode >= 3 && (kk & 1)) ? BN : 0), da0 + static_cast<uint64_t>(kk * (A_MN ? 128 : 2)),
+                           db0 + static_cast<uint64_t>(kk * (B_MN ? 128 : 2)), IDESC, (kb > kb0 || kk > 0) ? 1u : 0u);
+          umma_commit_warp(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (lane == 0) umma_commit(&tmem_full_bar[acc]);
+      if (p.debug_mode == 1) {
+        if (lane == 0) mbar_arrive(&tmem_full_bar[acc]);
+      } else {
+        umma_commit_warp(&tmem_full_bar[acc]);
+      }
       __syncwarp();
       if (++acc == GEMM_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
@@ -322,7 +335,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       if (++acc == GEMM_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
-    if (leader) tma_store_wait_all();
+    if (leader) tma_store_wait_read();   // smem may be released; the writes themselves complete before the grid does
   }
 
   tc_fence_before();
@@ -398,6 +411,10 @@ static int launch_gemm(const vb_gemm_args& a, int splits, cudaStream_t stream) {
     return VB_ERR_UNSUPPORTED;
   }
   p.stages = stages;
+  static const int debug_mode = getenv("VB_GEMM_DEBUG") ? atoi(getenv("VB_GEMM_DEBUG")) : 0;
+  static const int debug_stages = getenv("VB_GEMM_STAGES") ? atoi(getenv("VB_GEMM_STAGES")) : 0;
+  p.debug_mode = debug_mode;
+  if (debug_stages >= 2 && debug_stages < stages) p.stages = stages = debug_stages;
   const int smem_bytes = fixed + stages * STAGE_BYTES;
 
   static int attr_bytes = 0;
@@ -433,7 +450,9 @@ static void pick_config(const vb_gemm_args& a, int* bn_out, int* splits_out) {
   const bool can_split = a.d_is_f32 && a.accumulate;
   double best_cost = 1e30;
   int best_bn = 128, best_splits = 1;
-  const int bns[3] = {256, 128, 64};
+  // measured on B200 at the ViLBERT shapes: a UTCHMMA has a ~110-cycle floor, so 128-wide tiles lose little against
+  // 256-wide ones while doubling the number of tiles (these GEMMs are short of CTAs, not of MMA rate)
+  const int bns[3] = {128, 64, 256};
   for (int bi = 0; bi < 3; ++bi) {
     const int bn = bns[bi];
     if (a.block_n != 0 && a.block_n != bn) continue;
@@ -446,8 +465,10 @@ static void pick_config(const vb_gemm_args& a, int* bn_out, int* splits_out) {
       const long tiles = static_cast<long>(m_tiles) * n_tiles * s;
       const long waves = (tiles + sms - 1) / sms;
       const int kb = (total_kb + s - 1) / s;
-      // per-tile time ~ main loop (bn/64 units per k-block) + fixed epilogue/fill cost (in the same units)
-      const double tile_cost = kb * (bn / 64.0) + 6.0 + bn / 32.0 + (s > 1 ? bn / 16.0 : 0.0);
+      // per-tile time in SM cycles, fitted to tools/gemm_debug.py runs: a k-block (4 UTCHMMA) costs ~430 / 460 / 590
+      // cycles at BN = 64 / 128 / 256, the epilogue ~5 cycles per column plus a fixed part, TMA reduce-adds a bit more
+      const double kb_cost = bn == 64 ? 430.0 : (bn == 128 ? 460.0 : 590.0);
+      const double tile_cost = kb * kb_cost + 400.0 + 5.0 * bn + (s > 1 ? 3.0 * bn : 0.0);
       const double cost = waves * tile_cost;
       if (cost < best_cost * 0.97) { best_cost = cost; best_bn = bn; best_splits = s; }
     }

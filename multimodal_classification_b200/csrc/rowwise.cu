@@ -27,9 +27,9 @@ __device__ __forceinline__ void ld8f(const float* p, float (&v)[8]) {
 }
 // keep decisions of 8 consecutive elements starting at element index e (e % 8 == 0) of dropout site `site`
 __device__ __forceinline__ void keep8(uint64_t seed, uint32_t site, uint32_t e, uint32_t thr, bool (&k)[8]) {
-  const uint4 r0 = dropout_bits(seed, site, e >> 2), r1 = dropout_bits(seed, site, (e >> 2) + 1);
-  k[0] = r0.x >= thr; k[1] = r0.y >= thr; k[2] = r0.z >= thr; k[3] = r0.w >= thr;
-  k[4] = r1.x >= thr; k[5] = r1.y >= thr; k[6] = r1.z >= thr; k[7] = r1.w >= thr;
+  const uint32_t m = dropout_keep8(seed, site, e >> 3, thr);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) k[i] = (m >> i) & 1u;
 }
 
 constexpr int LN_WARPS = 8;
