@@ -69,12 +69,16 @@ typedef struct vb_gemm_args {
   int32_t accumulate;  /* fp32 output only: D += result (gradient accumulation / split-K) */
   int32_t act;         /* vb_act */
   int32_t aux_mode;    /* vb_aux_mode */
-  int32_t block_n;     /* 0 = auto; else 64 | 128 | 256 */
+  int32_t block_n;     /* 0 = auto; else a preferred tile width 64 | 96 | 128 | 192 | 256 (ignored when illegal for the layout) */
   int32_t splits;      /* 0 = auto (1 unless fp32+accumulate); >1 requires d_is_f32 && accumulate */
   int32_t max_ctas;    /* 0 = all SMs; otherwise cap the persistent grid (stream co-scheduling) */
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, void* stream);
+/* Profiling aid (tools/gemm_trace.py): when non-NULL, every CTA of later vb_gemm_bf16 launches writes 24 int64 clock64()
+ * stamps (entry, prologue done, dependency wait done, first load, loads done, first operands landed, MMAs issued, first /
+ * last accumulator ready, stores issued, staging drained, exit) to device_buffer[cta*24 ..].  NULL switches it off. */
+int vb_gemm_set_trace(void* device_buffer);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise bandwidth kernels (one warp per row, 16-byte accesses, fp32 math on bf16 storage).

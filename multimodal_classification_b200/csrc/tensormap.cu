@@ -50,7 +50,8 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_cache;
 
 static int encode_cached(CUtensorMap* out, const MapKey& key, uint32_t rank, const void* base, const cuuint64_t* dims,
                          const cuuint64_t* strides_bytes, const cuuint32_t* box,
-                         CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
+                         CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                         CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cache.find(key);
@@ -66,7 +67,7 @@ static int encode_cached(CUtensorMap* out, const MapKey& key, uint32_t rank, con
   }
   const cuuint32_t elem_strides[3] = {1, 1, 1};
   CUresult r = fn(out, dtype, rank, const_cast<void*>(base), dims, strides_bytes, box,
-                  elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     static thread_local char buf[256];
@@ -100,6 +101,16 @@ int make_tensor_map_2d_f32(CUtensorMap* out, const void* base, int64_t inner, in
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   return encode_cached(out, key, 2, base, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
+
+int make_tensor_map_2d_sw64(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                            int box_outer) {
+  MapKey key = {{reinterpret_cast<uint64_t>(base), (uint64_t)inner, (uint64_t)outer, (uint64_t)ld,
+                 (uint64_t)box_inner, (uint64_t)box_outer, 2, /*bf16, 64-byte swizzle*/ 64}};
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  return encode_cached(out, key, 2, base, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int make_tensor_map_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1, int64_t s2,

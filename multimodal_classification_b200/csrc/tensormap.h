@@ -12,6 +12,9 @@ int make_tensor_map_2d(CUtensorMap* out, const void* base, int64_t inner, int64_
 // fp32 variant (epilogue stores / reduce-adds of fp32 gradients); box_inner * 4 bytes must be <= 128.
 int make_tensor_map_2d_f32(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld,
                            int box_inner, int box_outer);
+// bf16 with the 64-byte swizzle (epilogue boxes of 32 columns = 64-byte rows); box_inner * 2 bytes must be <= 64.
+int make_tensor_map_2d_sw64(CUtensorMap* out, const void* base, int64_t inner, int64_t outer, int64_t ld,
+                            int box_inner, int box_outer);
 // bf16, [d2, d1, d0] with element strides (s2, s1, 1); 128-byte swizzle.
 int make_tensor_map_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1,
                        int64_t s2, int box0, int box1, int box2);

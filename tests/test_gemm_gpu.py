@@ -25,7 +25,7 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("m,n,k", SHAPES)
-@pytest.mark.parametrize("block_n", [0, 64, 128, 256])
+@pytest.mark.parametrize("block_n", [0, 64, 96, 128, 192, 256])
 def test_forward_layout(m, n, k, block_n):
     from multimodal_classification_b200 import ops
     a, b = _rand((m, k), 1), _rand((n, k), 2)

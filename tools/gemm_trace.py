@@ -1,0 +1,39 @@
+"""In-kernel timeline of one GEMM launch (clock64 stamps written by every CTA, see vb_gemm_set_trace)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multimodal_classification_b200 import ops, _lib
+from tools.bench_kernels import rnd, graph_time
+
+NAMES = ["entry", "prologue", "depwait", "load0", "loads_done", "operands0", "mma_issued", "acc0_ready", "accN_ready",
+         "stores_issued", "staging_drained", "exit", "ldtm0_done", "units_done", "proxy_fenced", "epi_synced", "store0_issued",
+         "prod_begin", "prod_empty_ok", "bars_inited", "tmem_alloced", "cta_synced"]
+
+def trace(name, m, n, k, **kw):
+    a, b = rnd(m, k), rnd(n, k)
+    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    buf = torch.zeros(160 * 24, dtype=torch.int64, device="cuda")
+    for _ in range(3):
+        ops.gemm(a, b, out, **kw)
+    torch.cuda.synchronize()
+    _lib.lib().vb_gemm_set_trace(buf.data_ptr())
+    ops.gemm(a, b, out, **kw)
+    torch.cuda.synchronize()
+    _lib.lib().vb_gemm_set_trace(None)
+    t = buf.view(160, 24).cpu()
+    used = t[:, 0] != 0
+    t = t[used]
+    rel = (t - t[:, :1]).float()
+    t_us = graph_time(lambda: ops.gemm(a, b, out, **kw))
+    print(f"{name} {m}x{n}x{k} {kw}: {t_us:.2f} us/launch in a graph, {int(used.sum())} CTAs; median cycles since entry (min..max):")
+    rows = []
+    for i, nm in enumerate(NAMES):
+        col = rel[:, i][t[:, i] != 0]
+        if col.numel():
+            rows.append((col.median().item(), nm, col.min().item(), col.max().item()))
+    for med, nm, lo, hi in sorted(rows):
+        print(f"   {nm:16s} {med:9.0f}  ({lo:.0f} .. {hi:.0f})")
+
+if __name__ == "__main__":
+    trace("t.attn_out", 2048, 768, 768)
+    trace("t.ffn1", 2048, 3072, 768)
