@@ -225,6 +225,15 @@ int vb_roi_align_nhwc(const void* x, const float* rois, void* y, int32_t num_roi
 /* AdaptiveAvgPool2d((1,1)) + flatten (:71-73): bf16 [r, s, c] -> fp32 [r, c] */
 int vb_avgpool_nhwc(const void* x, float* out, int32_t r, int32_t s, int32_t c, void* stream);
 
+/* Proposal selection (:251-293).  scores[i] = 1 - |((x2-x1)/img_w) * ((y2-y1)/img_h) - target_area| in the reference's fp32
+ * operation order (:262-270); vb_nms = torchvision.ops.nms(boxes, scores, iou_threshold) (:277) with the CPU kernel's
+ * semantics: stable descending sort of the scores, greedy suppression of IoU > threshold, kept indices in score order.
+ * Bit-exact: the scores of translated copies of one box size tie exactly and the tie order decides which boxes survive.
+ * boxes fp32 [n,4] (x1,y1,x2,y2); workspace int32 [2n]; keep int32 [n]; *num_keep int32 (all device). */
+int vb_box_area_score(const float* boxes, int32_t n, float img_w, float img_h, float target_area, float* scores, void* stream);
+int vb_nms(const float* boxes, const float* scores, int32_t n, float iou_threshold, int32_t* workspace, int32_t* keep,
+           int32_t* num_keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,8 @@ def _declare(l: C.CDLL) -> None:
         "vb_roi_pool_nhwc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
         "vb_roi_align_nhwc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, i32, i32, vp],
         "vb_avgpool_nhwc": [vp, vp, i32, i32, i32, vp],
+        "vb_box_area_score": [vp, i32, f32, f32, f32, vp, vp],
+        "vb_nms": [vp, vp, i32, f32, vp, vp, vp, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)

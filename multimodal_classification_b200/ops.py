@@ -309,3 +309,83 @@ def attention_bwd(dout, q, k, v, lse, dq, dk, dv, *, batch, heads, sq, sk, d, ma
     a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
     _lib.check(_lib.lib().vb_attention_bwd(C.byref(a), _stream()), "vb_attention_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ RoI feature stage
+def stem_im2col(img, out, kh=7, kw=7, stride=2, pad=3):
+    """conv1 operand of torchvision resnet152 (reference resnet152_roi.py:49): fp32 NCHW image -> bf16 [pixels, kpad]."""
+    _need_cuda(img, out)
+    n, c, h, w = img.shape
+    assert c == 3 and img.dtype == torch.float32 and img.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    _lib.check(_lib.lib().vb_stem_im2col(img.data_ptr(), out.data_ptr(), n, h, w, kh, kw, stride, pad, out.shape[1], _stream()),
+               "vb_stem_im2col")
+    return out
+
+
+def im2col_nhwc(x, out, kh, kw, stride, pad):
+    """bf16 NHWC [n,h,w,c] -> bf16 [n*ho*wo, kh*kw*c] (3x3 and strided 1x1 convolutions of the bottlenecks)."""
+    _need_cuda(x, out)
+    n, h, w, c = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and out.is_contiguous()
+    _lib.check(_lib.lib().vb_im2col_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, kh, kw, stride, pad, _stream()), "vb_im2col_nhwc")
+    return out
+
+
+def maxpool_nhwc(x, out, k=3, stride=2, pad=1):
+    _need_cuda(x, out)
+    n, h, w, c = x.shape
+    _lib.check(_lib.lib().vb_maxpool_nhwc(x.data_ptr(), out.data_ptr(), n, h, w, c, k, stride, pad, _stream()), "vb_maxpool_nhwc")
+    return out
+
+
+def roi_pool_nhwc(x, rois, out, spatial_scale, argmax=None):
+    """torchvision.ops.RoIPool on an NHWC bf16 map (reference resnet152_roi.py:126, 167-170); rois fp32 [r,5]."""
+    _need_cuda(x, rois, out, argmax)
+    n, h, w, c = x.shape
+    r, ph, pw, c2 = out.shape
+    assert c2 == c and rois.dtype == torch.float32 and rois.shape == (r, 5) and rois.is_contiguous()
+    _lib.check(_lib.lib().vb_roi_pool_nhwc(x.data_ptr(), rois.data_ptr(), out.data_ptr(), _ptr(argmax), r, n, h, w, c, ph, pw,
+                                           float(spatial_scale), _stream()), "vb_roi_pool_nhwc")
+    return out
+
+
+def roi_align_nhwc(x, rois, out, spatial_scale, sampling_ratio=2, aligned=False):
+    _need_cuda(x, rois, out)
+    n, h, w, c = x.shape
+    r, ph, pw, c2 = out.shape
+    assert c2 == c and rois.dtype == torch.float32 and rois.shape == (r, 5) and rois.is_contiguous()
+    _lib.check(_lib.lib().vb_roi_align_nhwc(x.data_ptr(), rois.data_ptr(), out.data_ptr(), r, n, h, w, c, ph, pw,
+                                            float(spatial_scale), int(sampling_ratio), int(aligned), _stream()), "vb_roi_align_nhwc")
+    return out
+
+
+def avgpool_nhwc(x, out):
+    """AdaptiveAvgPool2d((1,1)) + flatten: bf16 [r,s,c] -> fp32 [r,c]."""
+    _need_cuda(x, out)
+    r, s, c = x.shape
+    assert out.dtype == torch.float32 and out.shape == (r, c)
+    _lib.check(_lib.lib().vb_avgpool_nhwc(x.data_ptr(), out.data_ptr(), r, s, c, _stream()), "vb_avgpool_nhwc")
+    return out
+
+
+def box_area_score(boxes, img_w, img_h, scores, target=0.15):
+    _need_cuda(boxes, scores)
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.shape[1] == 4
+    _lib.check(_lib.lib().vb_box_area_score(boxes.data_ptr(), boxes.shape[0], float(img_w), float(img_h), float(target),
+                                            scores.data_ptr(), _stream()), "vb_box_area_score")
+    return scores
+
+
+def nms(boxes, scores, iou_threshold):
+    """torchvision.ops.nms with the CPU kernel's tie order; returns the kept indices (int64, score order)."""
+    _need_cuda(boxes, scores)
+    n = boxes.shape[0]
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and scores.dtype == torch.float32
+    if n == 0:
+        return torch.empty(0, dtype=torch.long, device=boxes.device)
+    ws = torch.empty(2 * max(n, 1), dtype=torch.int32, device=boxes.device)
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=boxes.device)
+    cnt = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    _lib.check(_lib.lib().vb_nms(boxes.data_ptr(), scores.data_ptr(), n, float(iou_threshold), ws.data_ptr(), keep.data_ptr(),
+                                 cnt.data_ptr(), _stream()), "vb_nms")
+    return keep[:int(cnt.item())].long()

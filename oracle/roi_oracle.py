@@ -1,0 +1,240 @@
+"""ORACLE (test infrastructure, never shipped, never on the product path).
+
+CPU, fp32 restatement of the reference's ResNet-152 RoI feature stage
+(/root/reference/src/multimodalclassification/models/feature_extractors/resnet152_roi.py), written as pure functions over a
+``state_dict`` with the reference backbone's key names (``base.0.weight``, ``base.4.0.conv1.weight``, ``top.2.bn3.bias``
+...) so that it travels to the GPU box (the reference itself does not).  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU legs may import it.
+
+Third-party arithmetic on this path (not under /root/reference; versions unpinned by the reference):
+torchvision 0.26 ``resnet152`` (Bottleneck v1.5: stride on the 3x3), ``ops.RoIPool`` and ``ops.nms``.  Their published
+algorithms are restated here (``roi_pool``, ``nms``: plain numpy loops following torchvision/csrc/ops/cpu/*.cpp).
+
+Pinning: the reference holds no golden vectors for this path, so ``oracle/make_golden_roi.py`` imports the
+reference extractor in the authoring container (torchvision weights replaced by ``seeded_backbone_state`` below, as there is
+no network for the ImageNet checkpoint), runs it on a seeded image and commits proposals / RoIPool / NMS / feature vectors
+under ``tests/golden/roi_*.npz``; ``tests/test_roi_oracle_cpu.py`` checks this file against them: bit-equal for boxes, NMS
+order, RoIPool and normalised boxes; <= 1e-4 relative for the fp32 features (different conv summation order).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LAYERS = (("base.4", 3, 64, 1), ("base.5", 8, 128, 2), ("base.6", 36, 256, 2), ("top", 3, 512, 2))   # torchvision resnet152
+
+
+# ------------------------------------------------------------------------------------------------ seeded weights
+def seeded_backbone_state(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Deterministic stand-in for the ImageNet checkpoint, keyed like the reference's ``ResNet152Backbone.state_dict()``.
+    He-normal convolutions; BatchNorm statistics and affine parameters drawn so that folding them is not a no-op; the last
+    BatchNorm of every bottleneck is damped so that 50 un-normalised residual additions keep activations O(1)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        sd[name + ".weight"] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
+
+    def bn(name, c, gain):
+        sd[name + ".weight"] = (0.75 + 0.5 * torch.rand(c, generator=g)) * gain
+        sd[name + ".bias"] = (torch.rand(c, generator=g) - 0.5) * 0.2
+        sd[name + ".running_mean"] = (torch.rand(c, generator=g) - 0.5) * 0.2
+        sd[name + ".running_var"] = 0.75 + 0.5 * torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    conv("base.0", 64, 3, 7)
+    bn("base.1", 64, 1.0)
+    cin = 64
+    for prefix, blocks, width, stride in LAYERS:
+        for b in range(blocks):
+            p = f"{prefix}.{b}"
+            conv(p + ".conv1", width, cin, 1); bn(p + ".bn1", width, 1.0)
+            conv(p + ".conv2", width, width, 3); bn(p + ".bn2", width, 1.0)
+            conv(p + ".conv3", width * 4, width, 1); bn(p + ".bn3", width * 4, 0.25)
+            if b == 0:
+                conv(p + ".downsample.0", width * 4, cin, 1); bn(p + ".downsample.1", width * 4, 0.7)
+            cin = width * 4
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------ ResNet-152 trunk
+def _bn(sd, name, x):
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
+                        training=False, eps=1e-5)
+
+
+def _bottleneck(sd, p, x, stride):
+    """torchvision.models.resnet.Bottleneck.forward (v1.5)."""
+    out = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"])))
+    out = F.relu(_bn(sd, p + ".bn2", F.conv2d(out, sd[p + ".conv2.weight"], stride=stride, padding=1)))
+    out = _bn(sd, p + ".bn3", F.conv2d(out, sd[p + ".conv3.weight"]))
+    if (p + ".downsample.0.weight") in sd:
+        x = _bn(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride))
+    return F.relu(out + x)
+
+
+def _layer(sd, prefix, blocks, stride, x):
+    for b in range(blocks):
+        x = _bottleneck(sd, f"{prefix}.{b}", x, stride if b == 0 else 1)
+    return x
+
+
+def forward_base(sd, img: torch.Tensor) -> torch.Tensor:
+    """resnet152_roi.py:49-57, 65-67: conv1, bn1, relu, maxpool, layer1..3.  [B,3,H,W] -> [B,1024,H/16,W/16]."""
+    x = F.relu(_bn(sd, "base.1", F.conv2d(img, sd["base.0.weight"], stride=2, padding=3)))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for prefix, blocks, _, stride in LAYERS[:3]:
+        x = _layer(sd, prefix, blocks, stride, x)
+    return x
+
+
+def forward_top(sd, pooled: torch.Tensor) -> torch.Tensor:
+    """resnet152_roi.py:69-74: layer4, global average pool, flatten.  [R,1024,p,p] -> [R,2048]."""
+    x = _layer(sd, "top", 3, 2, pooled)
+    return x.mean(dim=(2, 3))
+
+
+# ------------------------------------------------------------------------------------------------ RoIPool / NMS / boxes
+def _round_half_away(x: np.float32) -> int:
+    return int(math.floor(float(x) + 0.5)) if x >= 0 else -int(math.floor(-float(x) + 0.5))
+
+
+def roi_pool(fmap: np.ndarray, rois: np.ndarray, pooled: int, spatial_scale: float) -> np.ndarray:
+    """torchvision.ops.roi_pool (csrc/ops/cpu/roi_pool_kernel.cpp): fmap [N,C,H,W] fp32, rois [R,5] -> [R,C,p,p]."""
+    _, c, h, w = fmap.shape
+    out = np.zeros((rois.shape[0], c, pooled, pooled), dtype=np.float32)
+    ss = np.float32(spatial_scale)
+    for r, roi in enumerate(rois.astype(np.float32)):
+        b = int(roi[0])
+        x1, y1 = _round_half_away(roi[1] * ss), _round_half_away(roi[2] * ss)
+        x2, y2 = _round_half_away(roi[3] * ss), _round_half_away(roi[4] * ss)
+        rw, rh = max(x2 - x1 + 1, 1), max(y2 - y1 + 1, 1)
+        bh, bw = np.float32(rh) / np.float32(pooled), np.float32(rw) / np.float32(pooled)
+        for ph in range(pooled):
+            hs = min(max(int(math.floor(np.float32(ph) * bh)) + y1, 0), h)
+            he = min(max(int(math.ceil(np.float32(ph + 1) * bh)) + y1, 0), h)
+            for pw in range(pooled):
+                ws = min(max(int(math.floor(np.float32(pw) * bw)) + x1, 0), w)
+                we = min(max(int(math.ceil(np.float32(pw + 1) * bw)) + x1, 0), w)
+                if he > hs and we > ws:
+                    out[r, :, ph, pw] = fmap[b, :, hs:he, ws:we].reshape(c, -1).max(axis=1)
+    return out
+
+
+def nms(boxes: np.ndarray, scores: np.ndarray, thr: float) -> np.ndarray:
+    """torchvision.ops.nms, CPU kernel (csrc/ops/cpu/nms_kernel.cpp): stable descending sort, greedy, fp32 arithmetic."""
+    boxes = boxes.astype(np.float32)
+    x1, y1, x2, y2 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
+    areas = (x2 - x1) * (y2 - y1)
+    order = np.argsort(-scores.astype(np.float32), kind="stable")
+    suppressed = np.zeros(len(boxes), dtype=bool)
+    keep: List[int] = []
+    for oi, i in enumerate(order):
+        if suppressed[i]:
+            continue
+        keep.append(int(i))
+        rest = order[oi + 1:]
+        xx1, yy1 = np.maximum(x1[i], x1[rest]), np.maximum(y1[i], y1[rest])
+        xx2, yy2 = np.minimum(x2[i], x2[rest]), np.minimum(y2[i], y2[rest])
+        w = np.maximum(np.float32(0), xx2 - xx1)
+        h = np.maximum(np.float32(0), yy2 - yy1)
+        inter = w * h
+        ovr = inter / (areas[i] + areas[rest] - inter)
+        suppressed[rest[ovr > np.float32(thr)]] = True
+    return np.asarray(keep, dtype=np.int64)
+
+
+def grid_proposals(num_regions: int, img_h: int, img_w: int) -> np.ndarray:
+    """resnet152_roi.py:191-206."""
+    g = int(num_regions ** 0.5)
+    cell_h, cell_w = img_h / g, img_w / g
+    rows = []
+    for i in range(g):
+        for j in range(g):
+            rows.append([j * cell_w, i * cell_h, (j + 1) * cell_w, (i + 1) * cell_h])
+    return np.array(rows, dtype=np.float32).reshape(-1, 4)
+
+
+def multi_scale_candidates(img_h: int, img_w: int) -> np.ndarray:
+    """resnet152_roi.py:208-240 (Python-double accumulation, one rounding to fp32 at the end)."""
+    rows = []
+    for scale in (0.15, 0.25, 0.35, 0.5, 0.7):
+        for ar in (0.5, 0.75, 1.0, 1.33, 2.0):
+            box_w = img_w * scale
+            box_h = box_w / ar
+            box_h = min(box_h, img_h * 0.95)
+            box_w = min(box_w, img_w * 0.95)
+            stride_x, stride_y = max(box_w * 0.4, 20), max(box_h * 0.4, 20)
+            x = 0
+            while x + box_w <= img_w:
+                y = 0
+                while y + box_h <= img_h:
+                    rows.append([x, y, x + box_w, y + box_h])
+                    y += stride_y
+                x += stride_x
+    return np.array(rows, dtype=np.float32).reshape(-1, 4)
+
+
+def area_scores(boxes: np.ndarray, img_h: int, img_w: int) -> np.ndarray:
+    """resnet152_roi.py:262-270: 1 - |w/W * h/H - 0.15| in fp32, one rounding per operation."""
+    b = boxes.astype(np.float32)
+    widths = (b[:, 2] - b[:, 0]) / np.float32(img_w)
+    heights = (b[:, 3] - b[:, 1]) / np.float32(img_h)
+    return (np.float32(1.0) - np.abs(widths * heights - np.float32(0.15))).astype(np.float32)
+
+
+def proposals(num_regions: int, img_h: int, img_w: int, multi_scale: bool = True) -> np.ndarray:
+    """resnet152_roi.py:180-293."""
+    if not multi_scale:
+        return grid_proposals(num_regions, img_h, img_w)
+    boxes = multi_scale_candidates(img_h, img_w)
+    if len(boxes) > num_regions:
+        keep = nms(boxes, area_scores(boxes, img_h, img_w), 0.5)
+        if len(keep) < num_regions:
+            kept = set(keep.tolist())
+            rest = [i for i in range(len(boxes)) if i not in kept]
+            keep = np.concatenate([keep, np.asarray(rest[: num_regions - len(keep)], dtype=np.int64)])
+        boxes = boxes[keep[:num_regions]]
+    elif len(boxes) < num_regions:
+        boxes = np.concatenate([boxes, grid_proposals(num_regions, img_h, img_w)], axis=0)[:num_regions]
+    return boxes[:num_regions]
+
+
+def normalize_boxes(boxes: np.ndarray, img_w: int, img_h: int) -> np.ndarray:
+    """resnet152_roi.py:295-311."""
+    nb = boxes.astype(np.float32).copy()
+    nb[:, 0] /= np.float32(img_w); nb[:, 2] /= np.float32(img_w)
+    nb[:, 1] /= np.float32(img_h); nb[:, 3] /= np.float32(img_h)
+    nb = np.minimum(np.maximum(nb, np.float32(0)), np.float32(1))
+    areas = (nb[:, 2] - nb[:, 0]) * (nb[:, 3] - nb[:, 1])
+    return np.concatenate([nb, areas[:, None]], axis=1)
+
+
+# ------------------------------------------------------------------------------------------------ whole stage
+def extract_features(sd, img: torch.Tensor, num_regions: int = 36, roi_size: int = 14, multi_scale: bool = True
+                     ) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """resnet152_roi.py:144-178 on an already preprocessed image [1,3,H,W] (fp32): (features [N,2048], spatial [N,5], boxes)."""
+    h, w = img.shape[2], img.shape[3]
+    with torch.no_grad():
+        fmap = forward_base(sd, img)
+        boxes = proposals(num_regions, h, w, multi_scale)
+        rois = np.concatenate([np.zeros((len(boxes), 1), np.float32), boxes], axis=1)
+        pooled = roi_pool(fmap.numpy(), rois, roi_size, 1.0 / 16.0)
+        feats = forward_top(sd, torch.from_numpy(pooled))
+    return feats.numpy(), normalize_boxes(boxes, w, h), boxes
+
+
+def synthetic_image(seed: int = 7, h: int = 96, w: int = 128) -> np.ndarray:
+    """uint8 HxWx3 test picture: smooth gradients + blocks + noise (so that resizing, pooling and max selection all matter)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.stack([xx / w * 255, yy / h * 255, (xx + yy) / (h + w) * 255], axis=2)
+    for _ in range(12):
+        y0, x0 = rng.integers(0, h - 8), rng.integers(0, w - 8)
+        img[y0:y0 + rng.integers(4, 24), x0:x0 + rng.integers(4, 32)] = rng.integers(0, 255, size=3)
+    img += rng.normal(0, 12, size=img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)

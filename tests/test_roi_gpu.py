@@ -1,0 +1,170 @@
+"""ResNet-152 RoI feature stage on the GPU (through the C ABI) against the oracle and the reference's fixtures.
+
+Bit-exact: proposal boxes, NMS order, normalised boxes, RoIPool (index arithmetic and max selection).
+Floating point (bf16 activations, fp32 accumulation, 155 convolutions deep): features within 3e-2 of the fp32 reference,
+measured as max |delta| / max |ref| and as relative L2 -- the tolerance BASELINE.json's north_star states for bf16 (2e-2 on
+logits) widened for the depth of the trunk; single kernels are held to 2e-2 / exact as noted per test."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "roi_stage.npz"))
+SIZES = [tuple(int(v) for v in hw) for hw in G["proposal_sizes"]]
+
+
+def _nhwc_bf16(x):  # [N,C,H,W] fp32 -> NHWC bf16 cuda
+    return torch.from_numpy(np.ascontiguousarray(x)).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+@pytest.mark.parametrize("h,w", SIZES)
+def test_proposals_bit_exact(h, w):
+    from multimodal_classification_b200 import resnet152_roi as rr
+    dev = torch.device("cuda")
+    assert np.array_equal(rr.generate_proposals(36, h, w, True, dev).cpu().numpy(), G[f"boxes_ms_{h}x{w}"])
+    assert np.array_equal(rr.generate_proposals(36, h, w, False, dev).cpu().numpy(), G[f"boxes_grid_{h}x{w}"])
+    assert np.array_equal(rr.normalize_boxes(G[f"boxes_ms_{h}x{w}"], w, h), G[f"spatial_ms_{h}x{w}"])
+
+
+def test_nms_and_scores_bit_exact():
+    from multimodal_classification_b200 import ops
+    c = torch.from_numpy(G["nms_cands"]).cuda()
+    s = torch.empty(c.shape[0], device="cuda")
+    ops.box_area_score(c, 600, 600, s)
+    assert np.array_equal(s.cpu().numpy(), G["nms_scores"])
+    assert np.array_equal(ops.nms(c, s, 0.5).cpu().numpy(), G["nms_keep"])
+    rb, rs = torch.from_numpy(G["nms_rand_boxes"]).cuda(), torch.from_numpy(G["nms_rand_scores"]).cuda()
+    for thr in (0.3, 0.5, 0.7):
+        assert np.array_equal(ops.nms(rb, rs, thr).cpu().numpy(), G[f"nms_rand_keep_{int(thr * 10)}"])
+    assert ops.nms(rb[:0].contiguous(), rs[:0].contiguous(), 0.5).numel() == 0
+
+
+@pytest.mark.parametrize("p", [14, 7])
+def test_roi_pool_bit_exact(p):
+    """The fixture map is bf16-representable, so the bf16 kernel must reproduce torchvision's fp32 RoIPool exactly."""
+    from multimodal_classification_b200 import ops
+    x = _nhwc_bf16(G["roi_fmap"])
+    rois = torch.from_numpy(G["roi_rois"]).cuda()
+    out = torch.empty(rois.shape[0], p, p, x.shape[3], dtype=torch.bfloat16, device="cuda")
+    arg = torch.empty(out.shape, dtype=torch.int32, device="cuda")
+    ops.roi_pool_nhwc(x, rois, out, 1.0 / 16.0, argmax=arg)
+    got = out.float().permute(0, 3, 1, 2).cpu().numpy()
+    assert np.array_equal(got, G[f"roi_pool_{p}"])
+    # argmax points at an element holding the maximum (or -1 for an empty bin, whose value is 0)
+    a = arg.permute(0, 3, 1, 2).cpu().numpy()
+    fm = G["roi_fmap"]
+    r_idx = G["roi_rois"][:, 0].astype(int)
+    for r in (0, 5, 61, 63, 65):
+        for c in (0, 7, 23):
+            sel = a[r, c]
+            flat = fm[r_idx[r], c].reshape(-1)
+            ok = np.where(sel >= 0, flat[np.maximum(sel, 0)], 0.0)
+            assert np.array_equal(ok, got[r, c])
+
+
+def test_roi_align():
+    from multimodal_classification_b200 import ops
+    x = _nhwc_bf16(G["roi_fmap"])
+    rois = torch.from_numpy(G["roi_rois"]).cuda()
+    out = torch.empty(rois.shape[0], 7, 7, x.shape[3], dtype=torch.bfloat16, device="cuda")
+    ops.roi_align_nhwc(x, rois, out, 1.0 / 16.0, sampling_ratio=2, aligned=False)
+    ref = G["roi_align_7"]
+    err = np.abs(out.float().permute(0, 3, 1, 2).cpu().numpy() - ref).max()
+    assert err <= 2e-2 * np.abs(ref).max(), err
+
+
+def test_pooling_and_im2col_kernels():
+    from multimodal_classification_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 16, 13, 17, generator=g).to(torch.bfloat16).float()
+    xn = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    # max-pool 3/2/1: exact
+    ho, wo = (13 + 2 - 3) // 2 + 1, (17 + 2 - 3) // 2 + 1
+    out = torch.empty(2, ho, wo, 16, dtype=torch.bfloat16, device="cuda")
+    ops.maxpool_nhwc(xn, out)
+    assert torch.equal(out.float().permute(0, 3, 1, 2).cpu(), F.max_pool2d(x, 3, 2, 1))
+    # im2col 3x3 stride 2 pad 1 and 1x1 stride 2: exact gathers
+    for k, s, p in ((3, 2, 1), (3, 1, 1), (1, 2, 0)):
+        ho, wo = (13 + 2 * p - k) // s + 1, (17 + 2 * p - k) // s + 1
+        col = torch.empty(2 * ho * wo, k * k * 16, dtype=torch.bfloat16, device="cuda")
+        ops.im2col_nhwc(xn, col, k, k, s, p)
+        ref = F.unfold(x, k, padding=p, stride=s)                        # [N, C*k*k, L], row index c*k*k + ky*k + kx
+        ref = ref.view(2, 16, k * k, ho * wo).permute(0, 3, 2, 1).reshape(2 * ho * wo, k * k * 16)
+        assert torch.equal(col.float().cpu(), ref)
+    # stem im2col: fp32 NCHW image -> bf16 [pixels, 152]
+    img = torch.randn(2, 3, 30, 22, generator=g)
+    ho, wo = (30 + 6 - 7) // 2 + 1, (22 + 6 - 7) // 2 + 1
+    col = torch.full((2 * ho * wo, 152), 9.0, dtype=torch.bfloat16, device="cuda")
+    ops.stem_im2col(img.cuda(), col)
+    ref = F.unfold(img, 7, padding=3, stride=2).view(2, 3, 49, ho * wo).permute(0, 3, 2, 1).reshape(2 * ho * wo, 147)
+    assert torch.equal(col[:, :147].float().cpu(), ref.to(torch.bfloat16).float())
+    assert col[:, 147:].abs().max().item() == 0
+    # global average pool
+    y = torch.randn(5, 49, 64, generator=g).to(torch.bfloat16)
+    o = torch.empty(5, 64, device="cuda")
+    ops.avgpool_nhwc(y.cuda(), o)
+    assert torch.allclose(o.cpu(), y.float().mean(1), atol=1e-5)
+
+
+@pytest.fixture(scope="module")
+def extractor():
+    from multimodal_classification_b200.resnet152_roi import ResNet152ROIExtractor
+    from oracle import roi_oracle as ro
+    ext = ResNet152ROIExtractor(device="cuda", weights=None)
+    ext.backbone.load_state_dict(ro.seeded_backbone_state(0), strict=True)
+    return ext
+
+
+def test_state_dict_layout_matches_reference(extractor):
+    from oracle import roi_oracle as ro
+    assert list(extractor.backbone.state_dict().keys()) == list(ro.seeded_backbone_state(0).keys())
+
+
+def test_base_map_vs_oracle(extractor):
+    """conv1 .. layer3 (47 bottlenecks) on a small image against the fp32 oracle."""
+    from oracle import roi_oracle as ro
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(2, 3, 160, 192, generator=g)
+    with torch.no_grad():
+        ref = ro.forward_base(ro.seeded_backbone_state(0), img)
+    got = extractor.backbone.forward_base(img.cuda()).cpu()
+    assert got.shape == ref.shape
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel <= 3e-2, rel
+    assert (got - ref).abs().max().item() <= 3e-2 * ref.abs().max().item() + 3e-2 * ref.abs().mean().item()
+
+
+def test_extract_features_vs_reference(extractor):
+    from PIL import Image
+    feats, spatial = extractor.extract_features(Image.fromarray(G["image_u8"]))
+    assert feats.shape == (36, 2048) and spatial.shape == (36, 5) and feats.dtype == torch.float32
+    assert np.array_equal(spatial.cpu().numpy(), G["spatial"])
+    ref = G["features"]
+    got = feats.cpu().numpy()
+    rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    mx = np.abs(got - ref).max() / np.abs(ref).max()
+    print(f"features: rel-L2 {rel:.4f}  max-rel {mx:.4f}")
+    assert rel <= 2e-2 and mx <= 2e-2, (rel, mx)
+    # second call replays the captured graph: identical result
+    feats2, _ = extractor.extract_features(Image.fromarray(G["image_u8"]))
+    assert torch.equal(feats, feats2)
+
+
+def test_batched_forward_matches_single(extractor):
+    imgs = torch.stack([torch.from_numpy(G["image_u8"]).permute(2, 0, 1), torch.from_numpy(G["image_u8"][::-1].copy()).permute(2, 0, 1)])
+    f, s = extractor.forward(imgs)
+    assert f.shape == (2, 36, 2048) and s.shape == (2, 36, 5)
+    from PIL import Image
+    f0, _ = extractor.extract_features(Image.fromarray(G["image_u8"]))
+    assert (f[0] - f0).abs().max().item() <= 2e-2 * f0.abs().max().item()
+
+
+def test_cpu_device_is_refused():
+    from multimodal_classification_b200.resnet152_roi import ResNet152ROIExtractor
+    from multimodal_classification_b200._lib import VbError
+    with pytest.raises(VbError):
+        ResNet152ROIExtractor(device="cpu", weights=None)
