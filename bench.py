@@ -292,7 +292,10 @@ def main():
                                     "sample": f"median of {n} fwd+bwd passes of the oracle port over the same bs={B} batch, eval mode, fp32"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        vb_ddp.shutdown(model)
+        sys.stdout.flush()
+        os._exit(0)     # graphs that captured NCCL collectives can wedge interpreter teardown; the run is complete
 
 
 if __name__ == "__main__":

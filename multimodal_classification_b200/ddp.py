@@ -54,3 +54,21 @@ def broadcast_parameters(model, group=None, src: int = 0) -> None:
     with torch.no_grad():
         for p in model.parameters():
             dist.broadcast(p.data, src=src, group=group)
+
+
+def shutdown(*models, timeout_s: float = 10.0) -> bool:
+    """Tear the process group down at the end of a run.  CUDA graphs that captured NCCL collectives keep the communicator
+    busy, so the models' engines (and with them the graphs) are released first; ``destroy_process_group`` is then given
+    `timeout_s` seconds on a helper thread.  Returns False when it did not finish (the caller should then leave with
+    ``os._exit``: the work is done, only the teardown is stuck)."""
+    import gc
+    import threading
+    for m in models:
+        m._engine = None
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    return not t.is_alive()
