@@ -1,0 +1,23 @@
+"""Bind the B200 classes under the reference's own names.  Call ``install()`` once, before the
+reference's Kedro nodes run; no reference file is edited.
+
+The reference resolves the model inside ``_load_facebook_model`` (pipelines/model_training/nodes.py:223-230) from
+``multimodalclassification.models`` and the extractor through the dict literal in
+``models/feature_extractors/__init__.py:101-112`` / ``FEATURE_EXTRACTOR_REGISTRY`` (models/base.py:274)."""
+from __future__ import annotations
+
+
+def install() -> None:
+    import multimodalclassification.models as M
+    import multimodalclassification.models.base as B
+    import multimodalclassification.models.feature_extractors as FE
+    import multimodalclassification.models.vilbert_facebook_arch as A
+
+    from .resnet152_roi import ResNet152ROIExtractor
+    from .vilbert import ViLBERTForClassification, get_facebook_vilbert_config, load_facebook_weights
+
+    M.ViLBERTFacebookArch = A.ViLBERTForClassification = ViLBERTForClassification
+    M.get_facebook_vilbert_config = A.get_facebook_vilbert_config = get_facebook_vilbert_config
+    M.load_facebook_weights = A.load_facebook_weights = load_facebook_weights
+    FE.ResNet152ROIExtractor = ResNet152ROIExtractor
+    B.FEATURE_EXTRACTOR_REGISTRY["resnet152_roi"] = ResNet152ROIExtractor
