@@ -234,6 +234,26 @@ int vb_box_area_score(const float* boxes, int32_t n, float img_w, float img_h, f
 int vb_nms(const float* boxes, const float* scores, int32_t n, float iou_threshold, int32_t* workspace, int32_t* keep,
            int32_t* num_keep, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused optimizer step over the flat parameter / gradient buffers (next-row f-1 of SURVEY.md §8): replaces
+ * torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step() of pipelines/model_training/nodes.py:795-799.
+ *   vb_grad_sumsq : *acc += sum(grad[i]^2)  (fp64 device accumulator, zero it first; call once per contiguous range)
+ *   vb_adamw_step : g = grad * min(max_norm / (sqrt(*grad_sumsq) + 1e-6), 1) when max_norm > 0; decoupled weight decay; Adam
+ *                   moments; bias-corrected update (torch/optim/adam.py::_single_tensor_adam, fp32); and the bf16 shadow of
+ *                   the first shadow_n elements (the GEMM weights) rewritten in the same pass.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vb_adamw_args {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;   /* fp32 [n] */
+  void* shadow;                 /* bf16 [shadow_n] or NULL */
+  int64_t n, shadow_n;
+  const double* grad_sumsq;     /* device scalar from vb_grad_sumsq; required when max_norm > 0 */
+  float max_norm;               /* <= 0: no clipping */
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;                 /* 1-based step count (bias corrections) */
+} vb_adamw_args;
+int vb_grad_sumsq(const float* grad, int64_t n, double* acc, void* stream);
+int vb_adamw_step(const vb_adamw_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

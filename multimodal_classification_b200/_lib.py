@@ -66,6 +66,15 @@ class AttnArgs(C.Structure):
     ]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("shadow", C.c_void_p),
+        ("n", C.c_int64), ("shadow_n", C.c_int64), ("grad_sumsq", C.c_void_p), ("max_norm", C.c_float),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("step", C.c_int32),
+    ]
+
+
 DT_F32, DT_I32, DT_I64 = 0, 1, 2
 
 _lib = None
@@ -114,6 +123,8 @@ def _declare(l: C.CDLL) -> None:
         "vb_roi_pool_nhwc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
         "vb_roi_align_nhwc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, i32, i32, vp],
         "vb_avgpool_nhwc": [vp, vp, i32, i32, i32, vp],
+        "vb_grad_sumsq": [vp, i64, vp, vp],
+        "vb_adamw_step": [C.POINTER(AdamWArgs), vp],
         "vb_box_area_score": [vp, i32, f32, f32, f32, vp, vp],
         "vb_nms": [vp, vp, i32, f32, vp, vp, vp, vp],
     }
