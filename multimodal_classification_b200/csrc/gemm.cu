@@ -707,12 +707,16 @@ static int max_clusters(int cs, int occupancy) {
 // UMMA 128 x N x 16 (per SM) costs max(~110, N/2 + 20) cycles.
 struct TileChoice { int bn, cg, np, splits; };
 
-static double tile_cost(int bn, int cg, int np, int kb, double active_ctas, bool f32_out, bool split) {
+static double tile_cost(int bn, int cg, int np, int kb, double ctas, bool f32_out, bool split) {
+  // `ctas` CTAs run at once; when that is more than one per SM (two small CTAs co-resident) they share the SM's ingest
+  // bandwidth and tensor pipe
+  const double sms = ctas < num_sms() ? ctas : num_sms();
+  const double share = ctas / sms;
   const double a_bytes = GEMM_BM * 128.0, b_bytes = (bn / cg) * 128.0;
-  const double ingest = (a_bytes + b_bytes) / 58.0;
-  const double l2 = (a_bytes / np + b_bytes) * active_ctas / 6300.0;
-  const double mma_one = bn / 2.0 + 20.0;
-  const double mma = 4.0 * (mma_one < 110.0 ? 110.0 : mma_one);
+  const double ingest = (a_bytes + b_bytes) / 58.0 * share;
+  const double l2 = (a_bytes / np + b_bytes) * ctas / 6300.0;
+  const double mma_one = bn / (2.0 * (cg == 2 ? 1.0 : 1.0)) + 20.0;
+  const double mma = 4.0 * (mma_one < 110.0 ? 110.0 : mma_one) * share;
   double kb_cost = ingest > mma ? ingest : mma;
   if (l2 > kb_cost) kb_cost = l2;
   const double epi = 900.0 + (f32_out ? 6.0 : 4.0) * bn + (split ? 2.0 * bn : 0.0);
@@ -728,35 +732,39 @@ static bool tile_legal(const vb_gemm_args& a, int bn, int cg) {
 
 static TileChoice pick_config(const vb_gemm_args& a) {
   static const int force_np = getenv("VB_GEMM_NP") ? atoi(getenv("VB_GEMM_NP")) : 0;
-  const int cg = a.m > GEMM_BM ? 2 : 1;
-  const int m_tiles = (a.m + GEMM_BM * cg - 1) / (GEMM_BM * cg);
+  static const int force_cg = getenv("VB_GEMM_CG") ? atoi(getenv("VB_GEMM_CG")) : 0;
   const int total_kb = (a.k + GEMM_BK - 1) / GEMM_BK;
   const bool can_split = a.d_is_f32 && a.accumulate;
   double best_cost = 1e30;
-  TileChoice best = {128, cg, 1, 1};
+  TileChoice best = {128, a.m > GEMM_BM ? 2 : 1, 1, 1};
   const int bns[5] = {128, 96, 192, 256, 64};
   for (int pass = 0; pass < 2 && best_cost > 1e29; ++pass) {     // pass 1: the block_n hint was not legal, ignore it
-    for (int np = 1; np <= cg; ++np) {
-      if (force_np != 0 && cg == 2 && np != force_np) continue;
-      for (int bi = 0; bi < 5; ++bi) {
-        const int bn = bns[bi];
-        if (!tile_legal(a, bn, cg)) continue;
-        int clusters = max_clusters(cg * np, gemm_occupancy(bn));
-        if (a.max_ctas > 0 && a.max_ctas / (cg * np) < clusters) clusters = a.max_ctas / (cg * np) > 0 ? a.max_ctas / (cg * np) : 1;
-        if (pass == 0 && a.block_n != 0 && a.block_n != bn) continue;
-        if (bn > 64 && a.n <= bn / 2 && pass == 0 && a.block_n == 0) continue;  // do not waste most of a tile
-        const int n_tiles = ((a.n + bn - 1) / bn + np - 1) / np;                 // cluster steps along N
-        if (np == 2 && (a.n + bn - 1) / bn < 2) continue;
-        const int max_s = can_split ? 16 : 1;
-        for (int s = 1; s <= max_s; s *= 2) {
-          if (a.splits != 0 && a.splits != s) continue;
-          if (s > 1 && total_kb / s < 4) break;
-          const long tiles = static_cast<long>(m_tiles) * n_tiles * s;
-          const long waves = (tiles + clusters - 1) / clusters;
-          const int kb = (total_kb + s - 1) / s;
-          const double active = static_cast<double>(tiles < clusters ? tiles : clusters) * cg * np;
-          const double cost = waves * tile_cost(bn, cg, np, kb, active, a.d_is_f32 != 0, s > 1);
-          if (cost < best_cost * 0.97) { best_cost = cost; best = {bn, cg, np, s}; }
+    for (int cg = 2; cg >= 1; --cg) {
+      if (cg == 2 && a.m <= GEMM_BM) continue;                   // a pair would leave its second CTA without rows
+      if (force_cg != 0 && a.m > GEMM_BM && cg != force_cg) continue;
+      const int m_tiles = (a.m + GEMM_BM * cg - 1) / (GEMM_BM * cg);
+      for (int np = 1; np <= cg; ++np) {
+        if (force_np != 0 && cg == 2 && np != force_np) continue;
+        for (int bi = 0; bi < 5; ++bi) {
+          const int bn = bns[bi];
+          if (!tile_legal(a, bn, cg)) continue;
+          int clusters = max_clusters(cg * np, gemm_occupancy(bn));
+          if (a.max_ctas > 0 && a.max_ctas / (cg * np) < clusters) clusters = a.max_ctas / (cg * np) > 0 ? a.max_ctas / (cg * np) : 1;
+          if (pass == 0 && a.block_n != 0 && a.block_n != bn) continue;
+          if (bn > 64 && a.n <= bn / 2 && pass == 0 && a.block_n == 0) continue;  // do not waste most of a tile
+          const int n_tiles = ((a.n + bn - 1) / bn + np - 1) / np;                 // cluster steps along N
+          if (np == 2 && (a.n + bn - 1) / bn < 2) continue;
+          const int max_s = can_split ? 16 : 1;
+          for (int s = 1; s <= max_s; s *= 2) {
+            if (a.splits != 0 && a.splits != s) continue;
+            if (s > 1 && total_kb / s < 4) break;
+            const long tiles = static_cast<long>(m_tiles) * n_tiles * s;
+            const long waves = (tiles + clusters - 1) / clusters;
+            const int kb = (total_kb + s - 1) / s;
+            const double ctas = static_cast<double>(tiles < clusters ? tiles : clusters) * cg * np;
+            const double cost = waves * tile_cost(bn, cg, np, kb, ctas, a.d_is_f32 != 0, s > 1);
+            if (cost < best_cost * 0.97) { best_cost = cost; best = {bn, cg, np, s}; }
+          }
         }
       }
     }

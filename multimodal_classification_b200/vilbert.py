@@ -336,10 +336,11 @@ class _Engine:
         self.use_graphs = os.environ.get("VB_NO_GRAPH", "0") != "1"
         self.two_streams = os.environ.get("VB_ONE_STREAM", "0") != "1"
         self.side_streams = self.two_streams and os.environ.get("VB_NO_SIDE", "0") != "1"
+        self.wgrad_split = os.environ.get("VB_WGRAD_SPLIT", "0") == "1"   # measured slower in the full step (6.41 vs 5.91 ms): the 1 GB zero-fill evicts L2-resident activations
         self._pl = None
         self.launches = 0
         self.comm_group = getattr(model, "_ddp_group", None)   # data-parallel: see ddp.attach()
-        self.comm_stream = torch.cuda.Stream(device=device) if self.comm_group is not None else None
+        self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if self.comm_group is not None else None   # as urgent as the chain: NCCL CTAs must get SM slots while GEMMs are running
         self._site = 0
         f = self.flat
         for p in [f"bert.encoder.layer.{i}.attention.self" for i in range(self.cfg["num_hidden_layers"])] + \
@@ -369,7 +370,10 @@ class _Engine:
         if side is not None:
             side.wait_stream(cur)     # dy is complete on the chain stream
         with torch.cuda.stream(side if side is not None else cur):
-            ops.gemm(dy, x, f.g(wkey, shape=tuple(w.shape), numel=w.numel()), a_mn_major=True, b_mn_major=True)
+            # fp32 accumulate into the (pre-zeroed) flat gradient buffer: lets the GEMM split the long token dimension
+            # over more CTAs (TMA reduce-add), see run_backward
+            ops.gemm(dy, x, f.g(wkey, shape=tuple(w.shape), numel=w.numel()), a_mn_major=True, b_mn_major=True,
+                     accumulate=self.wgrad_split)
             if bias_grad:
                 bkey = wkey[:-len("weight")] + "bias"
                 ops.colsum(dy, f.g(bkey, numel=w.shape[0]))
@@ -633,6 +637,16 @@ class _Engine:
         sides_v = [pl.s_vw] if self.side_streams else []
         # gradients that are accumulated with atomics start from zero (biases, LayerNorm, location weights, tables)
         f.grad[f.w_end:f.s_end].zero_()
+        if self.wgrad_split:
+            # weight gradients are produced by split-K GEMMs that reduce-add into the buffer: zero it once, on the side
+            # stream(s) that own it, while the head of the backward chain runs
+            if self.side_streams:
+                pl.s_tw.wait_stream(s_t)
+                with torch.cuda.stream(pl.s_tw):
+                    f.grad[:f.w_end].zero_()
+                pl.s_vw.wait_stream(pl.s_tw)
+            else:
+                f.grad[:f.w_end].zero_()
         dy_t = [pl.buf("g.t_ping", (Mt, H)), pl.buf("g.t_pong", (Mt, H))]
         dy_v = [pl.buf("g.v_ping", (Mv, Hv)), pl.buf("g.v_pong", (Mv, Hv))]
         dy_t[0].zero_()
@@ -823,14 +837,12 @@ class _Step(torch.autograd.Function):
             plan.dloss.zero_()
         else:
             plan.dloss.copy_(g_loss.reshape(1))
-        flat = eng.flat
         carry = None
-        params = module._trainable_used()
-        if any(p.grad is not None for _, p in params):
-            carry = {k: p.grad.clone() for k, p in params if p.grad is not None}   # gradient accumulation (rare path)
+        params = module._grad_bindings()                     # [(key, parameter, view into the flat gradient buffer)], cached
+        if any(p.grad is not None for _, p, _ in params):
+            carry = {k: p.grad.clone() for k, p, _ in params if p.grad is not None}   # gradient accumulation (rare path)
         eng._execute(plan, "bwd")
-        for k, p in params:
-            g = flat.g(k)
+        for k, p, g in params:
             if carry is not None and k in carry:
                 g.add_(carry[k])
             p.grad = g
@@ -881,6 +893,17 @@ class ViLBERTForClassification(nn.Module):
     def _trainable_used(self):
         eng = self._engine
         return [(k, p) for k, p in eng.flat.named.items() if p.requires_grad and k in eng.flat.used]
+
+    def _grad_bindings(self):
+        """(key, parameter, gradient view) for every trainable parameter the forward uses; rebuilt only when the engine or a
+        requires_grad flag changes (building 469 views per backward costs more host time than the whole forward launch)."""
+        eng = self._engine
+        sig = (id(eng.flat), tuple(p.requires_grad for p in eng.flat.named.values()))
+        cache = getattr(eng, "_grad_cache", None)
+        if cache is None or cache[0] != sig:
+            cache = (sig, [(k, p, eng.flat.g(k)) for k, p in self._trainable_used()])
+            eng._grad_cache = cache
+        return cache[1]
 
     def _ensure_engine(self, device) -> _Engine:
         eng = self._engine

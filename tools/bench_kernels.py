@@ -70,7 +70,7 @@ def bench_gemms():
         else:
             t_d = graph_time(lambda: ops.gemm(dy, w, dx, b_mn_major=True, aux=aux, aux_mode=ops.AUX_ADD))
         t_dc = graph_time(lambda: torch.matmul(dy, w, out=dx))
-        t_w = graph_time(lambda: ops.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True))
+        t_w = graph_time(lambda: ops.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, accumulate=os.environ.get("VB_WGRAD_ACC", "0") == "1"))
         dwb = torch.empty(n, k, device="cuda", dtype=BF)
         t_wc = graph_time(lambda: torch.matmul(dy.t(), x, out=dwb))
         tf = lambda t: fl / t / 1e6
