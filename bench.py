@@ -210,8 +210,10 @@ def main():
     torch.manual_seed(0)
     model = ViLBERTForClassification(cfg, num_labels=2).to(dev)
     model.train(not args.eval_dropout_off)
-    if world > 1:
-        vb_ddp.attach(model, dist.group.WORLD)
+    if world > 1 and os.environ.get("VB_DDP_SKIP", "0") != "1":      # VB_DDP_SKIP: diagnostic only (replicas without exchange)
+        if os.environ.get("VB_DDP_FLUSH_MB"):
+            vb_ddp.FLUSH_BYTES = int(os.environ["VB_DDP_FLUSH_MB"]) << 20
+        vb_ddp.attach(model, dist.group.WORLD, compress=None if os.environ.get("VB_DDP_FP32", "0") == "1" else "bf16")
     host = vo.synthetic_batch(cfg, batch=B, seq=T, regions=R, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}

@@ -72,6 +72,8 @@ typedef struct vb_gemm_args {
   int32_t block_n;     /* 0 = auto; else a preferred tile width 64 | 96 | 128 | 192 | 256 (ignored when illegal for the layout) */
   int32_t splits;      /* 0 = auto (1 unless fp32+accumulate); >1 requires d_is_f32 && accumulate */
   int32_t max_ctas;    /* 0 = all SMs; otherwise cap the persistent grid (stream co-scheduling) */
+  int32_t b_streamed;  /* B is read once per step (a weight matrix): load it with the L2 evict-first hint */
+  int32_t d_streamed;  /* D is not re-read soon (a weight gradient): store it with the L2 evict-first hint */
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, void* stream);
@@ -148,6 +150,8 @@ int vb_colsum_bf16(const void* x, int64_t ld, int32_t m, int32_t n, float* out, 
  * device array of {const float* src; bf16* dst; int64 n}, block i converts 8192 elements of segs[block_seg[i]] starting
  * at block_off[i]. */
 int vb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* bf16 -> fp32 (data-parallel: gradient buckets are all-reduced in bf16 and widened back into the fp32 gradient buffer) */
+int vb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
 int vb_cast_f32_bf16_multi(const void* segs, const int32_t* block_seg, const int64_t* block_off, int32_t num_blocks,
                            void* stream);
 /* out = (1.0f - (float)mask) * -10000.0f, bit-exact with models/vilbert_facebook_arch.py:530-540 */

@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
         ("d_is_f32", C.c_int32), ("accumulate", C.c_int32), ("act", C.c_int32), ("aux_mode", C.c_int32),
         ("block_n", C.c_int32), ("splits", C.c_int32), ("max_ctas", C.c_int32),
+        ("b_streamed", C.c_int32), ("d_streamed", C.c_int32),
     ]
 
 
@@ -107,6 +108,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_gemm_set_trace": [vp],
         "vb_colsum_bf16": [vp, i64, i32, i32, vp, vp],
         "vb_cast_f32_bf16": [vp, vp, i64, vp],
+        "vb_cast_bf16_f32": [vp, vp, i64, vp],
         "vb_cast_f32_bf16_multi": [vp, vp, vp, i32, vp],
         "vb_mask_bias": [vp, i32, vp, i32, vp],
         "vb_i64_to_i32": [vp, vp, i32, i32, i32, vp, vp],

@@ -66,6 +66,7 @@ struct GemmKernelParams {
   int x_bytes;      // staging bytes for the aux-in / preact-out panel (0 = unused)
   int debug_mode;   // profiling only (VB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads; results are garbage
   uint32_t magic_m, magic_mn;   // fast_div multipliers for m_tiles and m_tiles * n_tiles
+  unsigned long long b_policy, d_policy;   // L2 eviction hints for the B loads / D stores
   long long* trace; // profiling only (vb_gemm_set_trace): 16 clock64 stamps per CTA, NULL in production
 };
 
@@ -207,6 +208,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   pin(p.d_is_f32); pin(p.reduce_add); pin(p.act); pin(p.aux_mode); pin(p.has_preact);
   pin(p.splits); pin(p.kb_per_split); pin(p.m_tiles); pin(p.n_tiles); pin(p.stages); pin(p.out_bytes); pin(p.x_bytes);
   pin(p.magic_m); pin(p.magic_mn);
+  asm volatile("" : "+l"(p.b_policy)); asm volatile("" : "+l"(p.d_policy));
   constexpr int BNL = BN / CG;                           // B rows (columns of the output) this CTA loads
   constexpr int CS = CG * NP;                            // CTAs per cluster: NP pairs, side by side along N, sharing A
   static_assert(CG == 2 || NP == 1, "multicast clusters are built from CTA pairs");
@@ -350,9 +352,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             if constexpr (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BNL / 64; ++j) tma_load_2d_pair(sb + j * (GEMM_BK * 128), &tma_b, bar, n0 + j * 64, k0);
+              for (int j = 0; j < BNL / 64; ++j) {
+                if (p.b_policy) tma_load_2d_pair_hint(sb + j * (GEMM_BK * 128), &tma_b, bar, n0 + j * 64, k0, p.b_policy);
+                else            tma_load_2d_pair(sb + j * (GEMM_BK * 128), &tma_b, bar, n0 + j * 64, k0);
+              }
             } else {
-              tma_load_2d_pair(sb, &tma_b, bar, k0, n0);
+              if (p.b_policy) tma_load_2d_pair_hint(sb, &tma_b, bar, k0, n0, p.b_policy);
+              else            tma_load_2d_pair(sb, &tma_b, bar, k0, n0);
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
@@ -364,9 +370,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
             if constexpr (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BNL / 64; ++j) tma_load_2d(sb + j * (GEMM_BK * 128), &tma_b, &full_bar[stage], n0 + j * 64, k0);
+              for (int j = 0; j < BNL / 64; ++j) {
+                if (p.b_policy) tma_load_2d_hint(sb + j * (GEMM_BK * 128), &tma_b, &full_bar[stage], n0 + j * 64, k0, p.b_policy);
+                else            tma_load_2d(sb + j * (GEMM_BK * 128), &tma_b, &full_bar[stage], n0 + j * 64, k0);
+              }
             } else {
-              tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+              if (p.b_policy) tma_load_2d_hint(sb, &tma_b, &full_bar[stage], k0, n0, p.b_policy);
+              else            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
             }
           }
           if (tile == first_tile && kb == kb0) trace_stamp(p, 3);
@@ -518,8 +528,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const int c0 = pn0 + ewarp * GEMM_CHUNK;
           if (c0 < p.n) {
             if (p.d_is_f32) {
-              if (p.reduce_add) tma_reduce_add_2d(&tma_d, stage_out + ewarp * GEMM_BOX_F32, c0, m0);
-              else              tma_store_2d(&tma_d, stage_out + ewarp * GEMM_BOX_F32, c0, m0);
+              if (p.d_policy) {
+                if (p.reduce_add) tma_reduce_add_2d_hint(&tma_d, stage_out + ewarp * GEMM_BOX_F32, c0, m0, p.d_policy);
+                else              tma_store_2d_hint(&tma_d, stage_out + ewarp * GEMM_BOX_F32, c0, m0, p.d_policy);
+              } else {
+                if (p.reduce_add) tma_reduce_add_2d(&tma_d, stage_out + ewarp * GEMM_BOX_F32, c0, m0);
+                else              tma_store_2d(&tma_d, stage_out + ewarp * GEMM_BOX_F32, c0, m0);
+              }
             } else {
               tma_store_2d(&tma_d, stage_out + ewarp * GEMM_BOX_BF16, c0, m0);
               if (p.has_preact) tma_store_2d(&tma_x, stage_x + ewarp * GEMM_BOX_BF16, c0, m0);
@@ -638,6 +653,9 @@ static int launch_gemm(const vb_gemm_args& a, int splits, cudaStream_t stream) {
   static const int debug_stages = getenv("VB_GEMM_STAGES") ? atoi(getenv("VB_GEMM_STAGES")) : 0;
   p.debug_mode = debug_mode;
   p.trace = g_trace;
+  static const bool hints = !(getenv("VB_GEMM_NO_L2_HINTS") && atoi(getenv("VB_GEMM_NO_L2_HINTS")) != 0);
+  p.b_policy = (hints && a.b_streamed) ? L2_EVICT_FIRST : 0ull;     // 0 = the plain (un-hinted) instruction
+  p.d_policy = (hints && a.d_streamed && a.d_is_f32) ? L2_EVICT_FIRST : 0ull;
   if (debug_stages >= 2 && debug_stages < stages) stages = debug_stages;
   p.stages = stages;
   const int smem_bytes = fixed + stages * STAGE_BYTES;
@@ -827,6 +845,15 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* args, void* stream) {
   VB_REQUIRE(!(a.d_is_f32 && a.d_preact != nullptr), "d_preact only with a bf16 output");
   VB_REQUIRE(!(a.d_preact != nullptr && a.aux_mode != VB_AUX_NONE), "d_preact and aux share one staging panel: use one of them");
   VB_REQUIRE(!(a.d_is_f32 && a.aux_mode != VB_AUX_NONE), "aux only with a bf16 output");
+  // VB_GEMM_MAX_CTAS: default cap of the persistent grid (data-parallel runs leave a few SMs to the NCCL kernels, so that a
+  // GEMM sized for the whole chip does not have to wait for SMs a collective is sitting on)
+  static const int env_max_ctas = getenv("VB_GEMM_MAX_CTAS") ? atoi(getenv("VB_GEMM_MAX_CTAS")) : 0;
+  vb_gemm_args capped;
+  if (a.max_ctas == 0 && env_max_ctas > 0) {
+    capped = a;
+    capped.max_ctas = env_max_ctas;
+    return vb_gemm_bf16(&capped, stream);
+  }
   const TileChoice c = pick_config(a);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (c.cg == 1) {

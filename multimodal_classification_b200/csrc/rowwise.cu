@@ -447,6 +447,21 @@ __global__ void cast_kernel(const float* src, __nv_bfloat16* dst, long long n) {
   }
 }
 
+// bf16 -> fp32 (gradient buckets coming back from the bf16 all-reduce)
+__global__ void uncast_kernel(const __nv_bfloat16* src, float* dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      ld8(src + i, v);
+      *reinterpret_cast<float4*>(dst + i) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      for (long long k = i; k < n; ++k) dst[k] = __bfloat162float(src[k]);
+    }
+  }
+}
+
 // additive attention mask, bit-exact restatement of (1.0 - m) * -10000.0 (vilbert_facebook_arch.py:530-540)
 template <typename T>
 __global__ void mask_bias_kernel(const T* m, float* out, int n) {
@@ -720,6 +735,15 @@ extern "C" int vb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* st
   long long blocks = (n + 256 * 8 - 1) / (256 * 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
   cast_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+extern "C" int vb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
+  VB_REQUIRE(src && dst && n > 0 && aligned16(src) && aligned16(dst), "bad cast arguments");
+  long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  uncast_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, n);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;
 }

@@ -41,12 +41,67 @@ def all_reduce_mean(t: torch.Tensor, group) -> None:
         t.mul_(1.0 / dist.get_world_size(group))
 
 
-def attach(model, group=None) -> None:
+def attach(model, group=None, compress: str = "bf16") -> None:
     """Make `model` (multimodal_classification_b200.vilbert.ViLBERTForClassification) average its gradients over
     `group` inside every backward pass.  Parameters must already be identical on all ranks (same seed / same
-    state_dict); call broadcast_parameters() otherwise."""
+    state_dict); call broadcast_parameters() otherwise.
+
+    compress="bf16" (default): every bucket is narrowed to bf16 by a cast kernel, all-reduced (498 MB instead of 995 MB per
+    step over NVLink) and widened back into the fp32 gradient buffer -- the usual bf16 gradient-compression trade (one extra
+    rounding of the averaged gradient, relative error <= 2^-8).  compress=None keeps the exchange in fp32."""
+    if compress not in (None, "bf16"):
+        raise ValueError("compress must be None or 'bf16'")
     model._ddp_group = group if group is not None else dist.group.WORLD
+    model._ddp_compress = compress
     model._engine = None
+
+
+FLUSH_BYTES = 160 << 20     # exchange finished buckets once this many gradient bytes are waiting
+
+
+def merge_ranges(ranges):
+    """Sorted union of [lo, hi) ranges (adjacent buckets of the flat buffer become one message)."""
+    out = []
+    for lo, hi in sorted(ranges):
+        if out and lo <= out[-1][1]:
+            out[-1][1] = max(out[-1][1], hi)
+        else:
+            out.append([lo, hi])
+    return [(lo, hi) for lo, hi in out]
+
+
+def all_reduce_mean_ranges(grad: torch.Tensor, ranges, group, staging=None) -> None:
+    """grad[lo:hi] <- mean over ranks for every range, as ONE coalesced collective launch.  With `staging` (a bf16 buffer
+    shaped like grad) the exchange is done in bf16: cast kernel -> all-reduce -> widening kernel."""
+    if staging is not None:
+        from . import ops
+        for lo, hi in ranges:
+            ops.cast_bf16(grad[lo:hi], staging[lo:hi])
+        msgs = [staging[lo:hi] for lo, hi in ranges]
+    else:
+        msgs = [grad[lo:hi] for lo, hi in ranges]
+    if len(msgs) == 1 or dist.get_backend(group) != "nccl":
+        for m in msgs:
+            all_reduce_mean(m, group)
+    else:
+        try:
+            with dist._coalescing_manager(group=group, device=grad.device, async_ops=False):
+                for m in msgs:
+                    dist.all_reduce(m, op=dist.ReduceOp.AVG, group=group)
+        except (AttributeError, TypeError):      # torch without the (private) coalescing manager: one launch per message
+            for m in msgs:
+                all_reduce_mean(m, group)
+    if staging is not None:
+        for lo, hi in ranges:
+            ops.cast_f32(staging[lo:hi], grad[lo:hi])
+
+
+def all_reduce_mean_bf16(grad: torch.Tensor, staging: torch.Tensor, group) -> None:
+    """grad (fp32, contiguous slice of the flat gradient buffer) <- mean over ranks, exchanged as bf16 through `staging`."""
+    from . import ops
+    ops.cast_bf16(grad, staging)
+    all_reduce_mean(staging, group)
+    ops.cast_f32(staging, grad)
 
 
 def broadcast_parameters(model, group=None, src: int = 0) -> None:

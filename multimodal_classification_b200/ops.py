@@ -29,7 +29,7 @@ def _need_cuda(*ts):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
          bias=None, scale=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, preact=None, accumulate=False,
-         block_n=0, splits=0, max_ctas=0) -> torch.Tensor:
+         block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False) -> torch.Tensor:
     """out[M,N] = epilogue(sum_k A(m,k) B(n,k)).
 
     a: [M,K] (K-major) or [K,M] (a_mn_major); b: [N,K] or [K,N] (b_mn_major); bf16, last dim contiguous.
@@ -67,6 +67,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     args.accumulate = int(accumulate)
     args.act, args.aux_mode = act, aux_mode
     args.block_n, args.splits, args.max_ctas = block_n, splits, max_ctas
+    args.b_streamed, args.d_streamed = int(b_streamed), int(d_streamed)
     _lib.check(_lib.lib().vb_gemm_bf16(C.byref(args), _stream()), "vb_gemm_bf16")
     return out
 
@@ -157,6 +158,14 @@ def cast_bf16(src, dst):
     assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.is_contiguous() and dst.is_contiguous()
     assert src.numel() == dst.numel()
     _lib.check(_lib.lib().vb_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "vb_cast_f32_bf16")
+    return dst
+
+
+def cast_f32(src, dst):
+    _need_cuda(src, dst)
+    assert src.dtype == torch.bfloat16 and dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    assert src.numel() == dst.numel()
+    _lib.check(_lib.lib().vb_cast_bf16_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "vb_cast_bf16_f32")
     return dst
 
 

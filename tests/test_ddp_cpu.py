@@ -64,14 +64,19 @@ def _worker(rank, world, port, q):
         flat.grad.copy_(torch.randn(flat.s_end, generator=g))
         mine = flat.grad.clone()
         order = ["tail"] + [n for n in flat.buckets if n != "tail"]
-        for name in reversed(order):
-            lo, hi = flat.buckets[name]
-            ddp.all_reduce_mean(flat.grad[lo:hi], dist.group.WORLD)
+        pending = []
+        for i, name in enumerate(reversed(order)):        # the engine queues finished buckets and exchanges them in groups
+            pending.append(flat.buckets[name])
+            if len(pending) == 3 or i == len(order) - 1:
+                ranges = ddp.merge_ranges(pending)
+                assert sum(hi - lo for lo, hi in ranges) == sum(hi - lo for lo, hi in pending)
+                ddp.all_reduce_mean_ranges(flat.grad, ranges, dist.group.WORLD)
+                pending = []
         others = [torch.randn(flat.s_end, generator=torch.Generator().manual_seed(7 + r)) for r in range(world)]
         want = torch.stack(others).mean(0)
         ok = torch.allclose(flat.grad, want, atol=1e-6) and torch.equal(others[rank], mine)
         ddp.attach(m, dist.group.WORLD)
-        q.put((rank, digest, bool(ok), m._ddp_group is not None and m._engine is None))
+        q.put((rank, digest, bool(ok), m._ddp_group is not None and m._engine is None and m._ddp_compress == "bf16"))
     finally:
         dist.destroy_process_group()
 

@@ -19,7 +19,8 @@ torch.manual_seed(0)
 model = ViLBERTForClassification(cfg, num_labels=2).to(dev).eval()
 solo = ViLBERTForClassification(cfg, num_labels=2).to(dev).eval()
 solo.load_state_dict(model.state_dict())
-ddp.attach(model, dist.group.WORLD)
+compress = None if os.environ.get("VB_DDP_FP32", "0") == "1" else "bf16"
+ddp.attach(model, dist.group.WORLD, compress=compress)
 batch = {k: v.to(dev) for k, v in vo.synthetic_batch(cfg, batch=4, seq=32, regions=20, seed=50 + rank).items()}
 say("built")
 for step in range(4):
@@ -40,7 +41,7 @@ for (k, p), (_, q) in zip(model.named_parameters(), solo.named_parameters()):
     dist.all_reduce(g, op=dist.ReduceOp.AVG)
     worst = max(worst, ((p.grad - g).abs().max() / (g.abs().max() + 1e-12)).item())
 say("worst relative gradient mismatch vs hand-averaged:", worst)
-assert worst < 1e-3, worst
+assert worst < (1e-3 if compress is None else 1e-2), worst      # bf16 exchange: one extra rounding (2^-8)
 dist.barrier()
 say("OK")
 clean = ddp.shutdown(model, solo)
