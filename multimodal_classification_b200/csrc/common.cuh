@@ -399,14 +399,16 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG for dropout.  The mask of element `idx` of dropout site `site` is a pure
+// Philox4x32-7 counter RNG for dropout (seven rounds: the smallest round count of the Philox family that passes BigCrush,
+// Salmon et al. SC'11 table 2; the usual ten add a safety margin that a dropout mask does not need, and the rounds are a
+// measurable share of the LayerNorm / attention kernels).  The mask of element `idx` of dropout site `site` is a pure
 // function of (seed, site, idx), so forward and backward regenerate it instead of storing it.
 // One Philox call yields 4 x 32 random bits = the keep decisions of 4 consecutive elements.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                             uint32_t k1) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < 7; ++i) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0;
