@@ -81,6 +81,9 @@ int vb_gemm_bf16(const vb_gemm_args* args, void* stream);
  * stamps (entry, prologue done, dependency wait done, first load, loads done, first operands landed, MMAs issued, first /
  * last accumulator ready, stores issued, staging drained, exit) to device_buffer[cta*24 ..].  NULL switches it off. */
 int vb_gemm_set_trace(void* device_buffer);
+/* Diagnostic (tools/gemm_occupancy.py): resident blocks per SM and co-resident 2-CTA clusters the runtime reports for the
+ * narrow-tile pair kernel at `smem_bytes` of dynamic shared memory. */
+int vb_gemm_debug_occupancy(int smem_bytes, int* blocks_per_sm, int* clusters);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-wise bandwidth kernels (one warp per row, 16-byte accesses, fp32 math on bf16 storage).

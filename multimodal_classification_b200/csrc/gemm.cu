@@ -19,6 +19,7 @@
 // launched with programmatic dependent launch: its prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps
 // the tail of the previous kernel on the stream, and griddepcontrol.wait precedes the first global access.
 // See include/vilbert_b200.h for the ABI.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -35,10 +36,12 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_ACC_STAGES = 2;
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_CHUNK = 32;            // epilogue granule: 32 accumulator columns = one staging box
-// Tiles up to 128 columns wide are built so that TWO CTAs fit on an SM (<= 112 KB smem, <= 102 registers, 256 TMEM columns):
-// with programmatic dependent launch the CTAs of the NEXT kernel of the stream are then already resident, past their
-// prologue, when this kernel drains, which removes the ~1.5 us launch gap + prologue from every link of a chain of ~6 us
-// GEMMs; and two tiles of one kernel on an SM overlap each other's epilogue.  Wider tiles need all 512 TMEM columns.
+// Tiles up to 128 columns wide use a compact configuration (<= 112 KB smem, <= 102 registers, 256 TMEM columns, two-chunk
+// staging panels) meant to let TWO CTAs share an SM, so that kernels of the concurrent text / visual / weight-gradient
+// streams overlap each other's prologue and epilogue.  Measured (tools/gemm_occupancy.py): the runtime still reports ONE
+// resident block per SM for this kernel whatever its shared-memory, register or thread budget (also with 6 warps / 96
+// registers), so the co-residency does not materialise on this driver; the compact configuration is kept because it is
+// the faster one in the full step (5.95 vs 6.15 ms).  Wider tiles need all 512 TMEM columns anyway.
 #ifdef VB_GEMM_OCC1
 __host__ __device__ constexpr int gemm_occupancy(int bn) { return 1; }
 #else
@@ -818,6 +821,26 @@ static int dispatch_bn(const vb_gemm_args& a, const TileChoice& c, cudaStream_t 
 
 }  // namespace vb
 
+// diagnostic: resident blocks per SM / co-resident 2-CTA clusters the runtime reports for the narrow-tile pair kernel at a given
+// dynamic shared-memory size (tools/gemm_occupancy.py)
+extern "C" int vb_gemm_debug_occupancy(int smem_bytes, int* blocks_per_sm, int* clusters) {
+  auto kern = vb::gemm_bf16_kernel<128, false, false, 2, 1>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, vb::GEMM_THREADS, smem_bytes) != cudaSuccess) return VB_ERR_CUDA;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148); cfg.blockDim = dim3(vb::GEMM_THREADS); cfg.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  if (cudaOccupancyMaxActiveClusters(clusters, kern, &cfg) != cudaSuccess) return VB_ERR_CUDA;
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, kern);
+  fprintf(stderr, "regs %d static smem %zu maxDyn %d\n", fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+  return VB_OK;
+}
+
 extern "C" int vb_gemm_set_trace(void* device_buffer) {
   vb::g_trace = static_cast<long long*>(device_buffer);
   return VB_OK;
@@ -855,6 +878,10 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* args, void* stream) {
     return vb_gemm_bf16(&capped, stream);
   }
   const TileChoice c = pick_config(a);
+  static const bool verbose = getenv("VB_GEMM_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "vb_gemm %dx%dx%d a_mn=%d b_mn=%d f32=%d -> bn=%d cg=%d np=%d splits=%d (clusters %d)\n", a.m, a.n, a.k, a.a_mn_major,
+            a.b_mn_major, a.d_is_f32, c.bn, c.cg, c.np, c.splits, max_clusters(c.cg * c.np, gemm_occupancy(c.bn)));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (c.cg == 1) {
     if (c.bn == 64) return dispatch_major<64, 1, 1>(a, c.splits, s);

@@ -9,9 +9,14 @@ NAMES = ["entry", "prologue", "depwait", "load0", "loads_done", "operands0", "mm
          "stores_issued", "staging_drained", "exit", "ldtm0_done", "units_done", "proxy_fenced", "epi_synced", "store0_issued",
          "prod_begin", "prod_empty_ok", "bars_inited", "tmem_alloced", "cta_synced"]
 
-def trace(name, m, n, k, **kw):
-    a, b = rnd(m, k), rnd(n, k)
-    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+def trace(name, m, n, k, wgrad=False, **kw):
+    if wgrad:      # dW[m,n] = dY[k,m]^T X[k,n]: both operands MN-major, fp32 output
+        a, b = rnd(k, m), rnd(k, n)
+        out = torch.zeros(m, n, device="cuda", dtype=torch.float32)
+        kw = dict(kw, a_mn_major=True, b_mn_major=True)
+    else:
+        a, b = rnd(m, k), rnd(n, k)
+        out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
     buf = torch.zeros(160 * 24, dtype=torch.int64, device="cuda")
     for _ in range(3):
         ops.gemm(a, b, out, **kw)
@@ -35,5 +40,11 @@ def trace(name, m, n, k, **kw):
         print(f"   {nm:16s} {med:9.0f}  ({lo:.0f} .. {hi:.0f})")
 
 if __name__ == "__main__":
-    trace("t.attn_out", 2048, 768, 768)
-    trace("t.ffn1", 2048, 3072, 768)
+    which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+    if which == "wgrad":
+        trace("t.ffn1 wgrad", 3072, 768, 2048, wgrad=True)
+        trace("t.attn_out wgrad", 768, 768, 2048, wgrad=True)
+        trace("t.ffn1 wgrad d_streamed", 3072, 768, 2048, wgrad=True, d_streamed=True)
+    else:
+        trace("t.attn_out", 2048, 768, 768)
+        trace("t.ffn1", 2048, 3072, 768)
