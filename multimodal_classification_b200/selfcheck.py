@@ -57,6 +57,28 @@ def compare_with_oracle(cfg, batch_kw, tol_logits=2e-2, check_grads=True, verbos
     return report
 
 
+def compare_roi_stage(verbose=True):
+    """ResNet-152 conv1..layer3 + RoIPool + layer4 on one small seeded image against the fp32 oracle (bit-exact boxes,
+    bf16 tolerance on the features)."""
+    from oracle import roi_oracle as ro
+    from .resnet152_roi import ResNet152ROIExtractor
+    import numpy as np
+    sd = ro.seeded_backbone_state(0)
+    ext = ResNet152ROIExtractor(device="cuda", weights=None, image_size=224)
+    ext.backbone.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(1, 3, 224, 224, generator=g)
+    feats, spatial = ext.extract_batch(img.cuda())
+    ref_f, ref_s, ref_boxes = ro.extract_features(sd, img)
+    assert np.array_equal(ext._generate_proposals(224, 224).cpu().numpy(), ref_boxes)
+    assert np.array_equal(spatial[0].cpu().numpy(), ref_s)
+    err = np.abs(feats[0].cpu().numpy() - ref_f).max() / np.abs(ref_f).max()
+    if verbose:
+        print(f"[selfcheck] RoI stage: boxes bit-exact, max|dfeat|/max|feat| = {err:.3e}")
+    assert err <= 2e-2, err
+    return err
+
+
 def smoke():
     if not torch.cuda.is_available():
         raise RuntimeError("smoke() needs a CUDA device")
@@ -65,4 +87,5 @@ def smoke():
     from oracle import vilbert_oracle as vo
     torch.cuda.set_device(0)
     compare_with_oracle(vo.tiny_config(), dict(batch=4, seq=128, regions=100, seed=1234))
+    compare_roi_stage()
     print("[selfcheck] smoke OK")
