@@ -242,6 +242,18 @@ int vb_nms(const float* boxes, const float* scores, int32_t n, float iou_thresho
            int32_t* num_keep, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * DINOv2 multi-layer fusion tail (next-row f-2; models/feature_extractors/dinov2_multilayer.py:342-381).
+ *   vb_bilinear_concat : torch.cat(layer_features, -1) -> [g x g grid] -> F.interpolate(size=(t,t), bilinear,
+ *                        align_corners=False) -> [batch*t*t, L*h] bf16.  layers: HOST array of L device pointers to fp32
+ *                        [batch, tokens, h] (strides in elements; first_token = 1 skips the CLS token, :320).
+ *   vb_gelu_bf16       : nn.GELU() (erf) between the LayerNorm and the second Linear of `projection` (:250-255).
+ * The two Linears are vb_gemm_bf16, the LayerNorm is vb_layernorm_fwd (eps 1e-5).
+ * ---------------------------------------------------------------------------------------------- */
+int vb_bilinear_concat(const float* const* layers, int32_t num_layers, void* out, int32_t batch, int32_t grid, int32_t target,
+                       int32_t h, int64_t batch_stride, int64_t token_stride, int32_t first_token, void* stream);
+int vb_gelu_bf16(const void* x, void* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused optimizer step over the flat parameter / gradient buffers (next-row f-1 of SURVEY.md §8): replaces
  * torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step() of pipelines/model_training/nodes.py:795-799.
  *   vb_grad_sumsq : *acc += sum(grad[i]^2)  (fp64 device accumulator, zero it first; call once per contiguous range)

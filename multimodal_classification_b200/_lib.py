@@ -125,6 +125,8 @@ def _declare(l: C.CDLL) -> None:
         "vb_roi_pool_nhwc": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp],
         "vb_roi_align_nhwc": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, i32, i32, vp],
         "vb_avgpool_nhwc": [vp, vp, i32, i32, i32, vp],
+        "vb_bilinear_concat": [vp, i32, vp, i32, i32, i32, i32, i64, i64, i32, vp],
+        "vb_gelu_bf16": [vp, vp, i64, vp],
         "vb_grad_sumsq": [vp, i64, vp, vp],
         "vb_adamw_step": [C.POINTER(AdamWArgs), vp],
         "vb_box_area_score": [vp, i32, f32, f32, f32, vp, vp],

@@ -238,3 +238,44 @@ def synthetic_image(seed: int = 7, h: int = 96, w: int = 128) -> np.ndarray:
         img[y0:y0 + rng.integers(4, 24), x0:x0 + rng.integers(4, 32)] = rng.integers(0, 255, size=3)
     img += rng.normal(0, 12, size=img.shape)
     return np.clip(img, 0, 255).astype(np.uint8)
+
+
+# ------------------------------------------------------------------------------------------------ DINOv2 fusion tail (f-2)
+def dinov2_fusion_tail(layer_features, proj_sd, num_regions: int = 36):
+    """models/feature_extractors/dinov2_multilayer.py:342-381 (fusion_strategy="concat") for patch features WITHOUT the CLS
+    token: L x [1, P, hidden] -> [num_regions, out].  proj_sd holds projection.{0,1,3}.{weight,bias}."""
+    fused = torch.cat(list(layer_features), dim=-1)
+    num_patches, dim = fused.shape[1], fused.shape[-1]
+    g, t = int(num_patches ** 0.5), int(num_regions ** 0.5)
+    grid = fused.permute(0, 2, 1).reshape(1, dim, g, g)
+    resized = F.interpolate(grid, size=(t, t), mode="bilinear", align_corners=False)
+    flat = resized.permute(0, 2, 3, 1).reshape(-1, dim)
+    y = F.linear(flat, proj_sd["projection.0.weight"], proj_sd["projection.0.bias"])
+    y = F.layer_norm(y, (y.shape[-1],), proj_sd["projection.1.weight"], proj_sd["projection.1.bias"], 1e-5)
+    y = F.gelu(y)
+    return F.linear(y, proj_sd["projection.3.weight"], proj_sd["projection.3.bias"])
+
+
+def grid_spatial(num_regions: int) -> np.ndarray:
+    """dinov2_multilayer.py:383-403."""
+    g = int(num_regions ** 0.5)
+    out = np.zeros((num_regions, 5), np.float32)
+    for i in range(g):
+        for j in range(g):
+            x1, y1, x2, y2 = j / g, i / g, (j + 1) / g, (i + 1) / g
+            out[i * g + j] = np.array([x1, y1, x2, y2, (x2 - x1) * (y2 - y1)], dtype=np.float32)
+    return out
+
+
+def seeded_fusion_inputs(seed: int = 21, layers: int = 4, grid: int = 37, hidden: int = 1024, out_dim: int = 2048):
+    """Seeded stand-ins for the ViT layer outputs and the projection parameters (no hub checkpoint offline)."""
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(1, grid * grid, hidden, generator=g) for _ in range(layers)]
+    k = layers * hidden
+    sd = {"projection.0.weight": (torch.rand(out_dim, k, generator=g) * 2 - 1) * math.sqrt(6.0 / (k + out_dim)),
+          "projection.0.bias": (torch.rand(out_dim, generator=g) - 0.5) * 0.1,
+          "projection.1.weight": 0.75 + 0.5 * torch.rand(out_dim, generator=g),
+          "projection.1.bias": (torch.rand(out_dim, generator=g) - 0.5) * 0.2,
+          "projection.3.weight": (torch.rand(out_dim, out_dim, generator=g) * 2 - 1) * math.sqrt(6.0 / (2 * out_dim)),
+          "projection.3.bias": (torch.rand(out_dim, generator=g) - 0.5) * 0.1}
+    return feats, sd

@@ -1,0 +1,59 @@
+"""DINOv2 multi-layer fusion tail: oracle vs the fixture produced by the reference's own code
+(oracle/make_golden_dinov2.py), and the CUDA path vs the same fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "dinov2_tail.npz"))
+
+
+def test_oracle_matches_reference_fixture():
+    from oracle import roi_oracle as ro
+    feats, sd = ro.seeded_fusion_inputs()
+    with torch.no_grad():
+        out = ro.dinov2_fusion_tail(feats, sd, 36).numpy()
+    assert np.abs(out - G["projected"]).max() <= 1e-5 * np.abs(G["projected"]).max()
+    assert np.array_equal(ro.grid_spatial(36), G["spatial"])
+
+
+@pytest.mark.gpu
+def test_cuda_tail_matches_reference_fixture():
+    from multimodal_classification_b200.dinov2_fusion import DINOv2FusionTail
+    from oracle import roi_oracle as ro
+    feats, sd = ro.seeded_fusion_inputs()
+    tail = DINOv2FusionTail(num_layers=4, hidden_size=1024, output_dim=2048, num_regions=36, device="cuda")
+    assert list(tail.state_dict().keys()) == list(sd.keys())
+    tail.load_state_dict(sd, strict=True)
+    out, spatial = tail.fuse([f.cuda() for f in feats])
+    assert out.shape == (1, 36, 2048) and out.dtype == torch.float32
+    assert np.array_equal(spatial[0].cpu().numpy(), G["spatial"])
+    ref = G["projected"]
+    err = np.abs(out[0].cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err <= 2e-2, err                      # bf16 operands, fp32 accumulation (north-star tolerance)
+    # CLS-first layout (what the ViT hooks capture, dinov2_multilayer.py:318-321) and a batch of two
+    with_cls = [torch.cat([torch.zeros(1, 1, 1024), f], dim=1).repeat(2, 1, 1).cuda() for f in feats]
+    out2, _ = tail.fuse(with_cls, has_cls=True)
+    assert out2.shape == (2, 36, 2048)
+    assert torch.allclose(out2[0], out[0], atol=1e-6) and torch.allclose(out2[1], out[0], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_bilinear_concat_kernel_vs_interpolate():
+    """The gather alone against F.interpolate(bilinear, align_corners=False) on the CPU, exact up to the bf16 rounding of
+    the output."""
+    import ctypes as C
+    from multimodal_classification_b200 import _lib
+    g = torch.Generator().manual_seed(1)
+    for grid, target, h, layers, b in ((37, 6, 64, 2, 2), (16, 7, 32, 3, 1), (5, 5, 8, 1, 1)):
+        feats = [torch.randn(b, grid * grid, h, generator=g) for _ in range(layers)]
+        fused = torch.cat(feats, -1)
+        ref = torch.nn.functional.interpolate(fused.permute(0, 2, 1).reshape(b, layers * h, grid, grid), size=(target, target),
+                                              mode="bilinear", align_corners=False).permute(0, 2, 3, 1).reshape(-1, layers * h)
+        dev = [f.cuda() for f in feats]
+        out = torch.empty(b * target * target, layers * h, dtype=torch.bfloat16, device="cuda")
+        ptrs = (C.c_void_p * layers)(*[f.data_ptr() for f in dev])
+        _lib.check(_lib.lib().vb_bilinear_concat(ptrs, layers, out.data_ptr(), b, grid, target, h, grid * grid * h, h, 0,
+                                                 torch.cuda.current_stream().cuda_stream), "vb_bilinear_concat")
+        assert torch.equal(out.float().cpu(), ref.to(torch.bfloat16).float())
