@@ -1,4 +1,4 @@
-"""GEMM main-loop dissection (VB_GEMM_DEBUG=1 no MMA / 2 no TMA; VB_GEMM_STAGES=n)."""
+"""GEMM main-loop dissection (library built with -DVB_GEMM_TRACE; VB_GEMM_DEBUG=1 no MMA / 2 no TMA; VB_GEMM_STAGES=n)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
