@@ -312,7 +312,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     // ------------------------------------------------------------------ TMA producer (one per CTA)
     if (lane == 0) {
       trace_stamp(p, 17);
-      int stage = 0;
+      int stage = 0, fills = 0;
       uint32_t phase = 0;
       const uint32_t full_leader = CG == 2 ? mapa_u32(&full_bar[0], leader_rank) : 0u;
       const uint16_t a_mask = static_cast<uint16_t>((1u << prank) | (1u << (prank + 2)));   // me and my twin in the other pair
@@ -323,7 +323,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int kb0 = tc.split * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (fills >= STAGES) mbar_wait(&empty_bar[stage], phase ^ 1u);   // the first pass over the ring needs no wait
+          ++fills;
           if (tile == first_tile && kb == kb0) trace_stamp(p, 18);
 #ifdef VB_GEMM_TRACE
           if (p.debug_mode == 2) {
@@ -395,14 +396,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint16_t pair_mask = static_cast<uint16_t>(3u << (pair * 2));          // accumulators are per pair
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
+      int acc = 0, tiles_done = 0;
       uint32_t acc_phase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
         const int split = static_cast<int>(fast_div(static_cast<uint32_t>(tile), p.magic_mn));
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
-        tc_fence_after();
+        if (tiles_done >= GEMM_ACC_STAGES) {                      // both accumulator stages start out free
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+          tc_fence_after();
+        }
+        ++tiles_done;
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
