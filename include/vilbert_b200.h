@@ -119,6 +119,10 @@ typedef struct vb_layernorm_args {
   float p_in, p_out;    /* dropout probabilities (0 = off) */
   uint32_t site_in, site_out;
   const uint64_t* seed; /* device pointer, may be NULL when both p are 0 */
+  /* fp32 residual stream (optional): the residual is read from res_f32 instead of res when given, and the output is ALSO
+   * written in fp32 to y_f32, so that consecutive blocks hand the residual over unrounded (what PyTorch's bf16 autocast does:
+   * LayerNorm and the residual add stay fp32, only the GEMM operands are bf16).  Leading dimensions in elements. */
+  const float* res_f32; float* y_f32; int64_t ldres_f32, ldy_f32;
 } vb_layernorm_args;
 int vb_layernorm_fwd(const vb_layernorm_args* args, void* stream);
 int vb_layernorm_bwd(const vb_layernorm_args* args, void* stream);
@@ -143,6 +147,7 @@ typedef struct vb_embed_args {
   float eps, p_out;
   uint32_t site_out;
   const uint64_t* seed;
+  float* y_f32;             /* optional fp32 copy of y [b*t,h] (residual stream) */
 } vb_embed_args;
 int vb_embed_text_fwd(const vb_embed_args* args, void* stream);
 int vb_embed_text_bwd(const vb_embed_args* args, void* stream);

@@ -41,6 +41,7 @@ class LayerNormArgs(C.Structure):
         ("lddres", C.c_int64),
         ("m", C.c_int32), ("h", C.c_int32), ("eps", C.c_float), ("p_in", C.c_float), ("p_out", C.c_float),
         ("site_in", C.c_uint32), ("site_out", C.c_uint32), ("seed", C.c_void_p),
+        ("res_f32", C.c_void_p), ("y_f32", C.c_void_p), ("ldres_f32", C.c_int64), ("ldy_f32", C.c_int64),
     ]
 
 
@@ -51,7 +52,7 @@ class EmbedArgs(C.Structure):
         ("dy", C.c_void_p), ("dword", C.c_void_p), ("dpos", C.c_void_p), ("dtype", C.c_void_p), ("dgamma", C.c_void_p),
         ("dbeta", C.c_void_p),
         ("b", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("vocab", C.c_int32), ("eps", C.c_float),
-        ("p_out", C.c_float), ("site_out", C.c_uint32), ("seed", C.c_void_p),
+        ("p_out", C.c_float), ("site_out", C.c_uint32), ("seed", C.c_void_p), ("y_f32", C.c_void_p),
     ]
 
 

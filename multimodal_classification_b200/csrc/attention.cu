@@ -1,6 +1,7 @@
 // Fused softmax attention on tcgen05 / TMEM for the short sequences of ViLBERT (<= 128 queries, <= 128 keys per
-// (sample, head); head width 64 or 128).  One CTA per (sample, head), 128 threads, thread i owns query row i
-// (= TMEM lane i), so the softmax needs no cross-thread reduction.
+// (sample, head); head width 64 or 128).  One CTA per (sample, head), 256 threads: two threads per query row (= TMEM lane),
+// each owning 64 of the 128 key columns, so the softmax needs one exchange of (max, sum) per row through shared memory and the
+// per-thread register tile is half a row (the 128-wide per-thread row of the first version was the critical path).
 //
 //   forward   S = Q K^T (UMMA 128x128xD) -> softmax(S*scale + mask) [+ dropout] -> P (bf16, swizzled smem) -> O = P V
 //   backward  recompute S and dP' = dO V^T -> P, dS in smem -> dV = P^T dO, dK = dS^T Q, dQ = dS K  (5 UMMAs total)
@@ -29,36 +30,34 @@ struct AttnKernelParams {
   const unsigned long long* seed;
 };
 
-// one full 128-column accumulator row of this thread (4 x tcgen05.ld.32x32b.x32, one wait)
-__device__ __forceinline__ void tmem_ld_row128(uint32_t taddr, float (&s)[128]) {
-  uint32_t r0[32], r1[32], r2[32], r3[32];
+constexpr int ATT_THREADS = 256;   // two threads per query row: thread (row, ch) owns key columns [64*ch, 64*ch + 64)
+
+// 64 accumulator columns of this thread's row (2 x tcgen05.ld.32x32b.x32, one wait)
+__device__ __forceinline__ void tmem_ld_row64(uint32_t taddr, float (&s)[64]) {
+  uint32_t r0[32], r1[32];
   tmem_ld_32x32(taddr, r0);
   tmem_ld_32x32(taddr + 32, r1);
-  tmem_ld_32x32(taddr + 64, r2);
-  tmem_ld_32x32(taddr + 96, r3);
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]);
-    s[64 + i] = __uint_as_float(r2[i]); s[96 + i] = __uint_as_float(r3[i]);
-  }
+  for (int i = 0; i < 32; ++i) { s[i] = __uint_as_float(r0[i]); s[32 + i] = __uint_as_float(r1[i]); }
 }
 
-// write 128 fp32 values of this thread's row as bf16 into a [128][2 x 64] swizzled tile pair
-__device__ __forceinline__ void store_row_bf16(uint8_t* tile, int row, const float (&v)[128]) {
+// write 64 fp32 values of this thread's half row as bf16 into one [128][64] 128B-swizzled tile
+__device__ __forceinline__ void store_half_row_bf16(uint8_t* tile, int row, const float (&v)[64]) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int j = 0; j < 8; ++j) {
     uint4 u;
     u.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); u.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
     u.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); u.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-    *reinterpret_cast<uint4*>(tile + (j >> 3) * ATT_CHUNK + swz128(row, j & 7)) = u;
+    *reinterpret_cast<uint4*>(tile + swz128(row, j)) = u;
   }
 }
 
-template <int D>
-__device__ __forceinline__ void store_tmem_rows(uint32_t taddr, __nv_bfloat16* dst, bool ok) {
+// NC32 x 32 accumulator columns of this thread's row -> bf16 global
+template <int NC32>
+__device__ __forceinline__ void store_tmem_cols(uint32_t taddr, __nv_bfloat16* dst, bool ok) {
 #pragma unroll
-  for (int c = 0; c < D / 32; ++c) {
+  for (int c = 0; c < NC32; ++c) {
     uint32_t r[32];
     tmem_ld_32x32(taddr + c * 32, r);
     tmem_ld_wait();
@@ -76,20 +75,21 @@ __device__ __forceinline__ void store_tmem_rows(uint32_t taddr, __nv_bfloat16* d
   }
 }
 
-// 128-bit keep mask of one query row (bit k = key k is kept)
-__device__ __forceinline__ void attn_keep_bits(uint64_t seed, uint32_t site, uint32_t row_index, uint32_t thr,
-                                               uint32_t (&keep)[4]) {
+// 64-bit keep mask of half a query row: words 2*ch and 2*ch+1 of the row's 128-bit mask (bit k = key k is kept); the Philox
+// counters are those of the whole-row mask, so forward and backward (and both halves) agree
+__device__ __forceinline__ void attn_keep_half(uint64_t seed, uint32_t site, uint32_t row_index, uint32_t thr, int ch,
+                                               uint32_t (&keep)[2]) {
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
+  for (int w = 0; w < 2; ++w) {
     uint32_t m = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) m |= dropout_keep8(seed, site, row_index * 16u + w * 4 + q, thr) << (q * 8);
+    for (int q = 0; q < 4; ++q) m |= dropout_keep8(seed, site, row_index * 16u + (2 * ch + w) * 4 + q, thr) << (q * 8);
     keep[w] = m;
   }
 }
 
 template <int D>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnKernelParams p) {
   constexpr int NC = D / 64;
@@ -101,10 +101,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sV = sK + NC * ATT_CHUNK;
   uint8_t* sP = sV + NC * ATT_CHUNK;
   float* sBias = reinterpret_cast<float*>(sP + 2 * ATT_CHUNK);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
+  float2* sRed = reinterpret_cast<float2*>(sBias + 128);          // [256] (max, sum) of every half row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + ATT_THREADS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, ch = tid >> 7;
   const int h = blockIdx.x, b = blockIdx.y;
 
   if (tid == 0) {
@@ -114,7 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.sk + tid] : 0.f) : -INFINITY;
+  if (tid < 128) sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.sk + tid] : 0.f) : -INFINITY;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -143,28 +145,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncwarp();
   tc_fence_after();
 
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  float s[128];
-  tmem_ld_row128(trow, s);
+  // thread (row, ch): TMEM lane = row (sub-partition warp & 3), columns [64 ch, 64 ch + 64)
+  const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  float s[64];
+  tmem_ld_row64(trow + ch * 64, s);
   float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 128; ++i) { s[i] = s[i] * p.scale + sBias[i]; mx = fmaxf(mx, s[i]); }
+  for (int i = 0; i < 64; ++i) { s[i] = s[i] * p.scale + sBias[ch * 64 + i]; mx = fmaxf(mx, s[i]); }
+  const float mx_safe = mx == -INFINITY ? 0.f : mx;   // a half row with no valid key (sk <= 64): every term is exp(-inf) = 0
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 128; ++i) { s[i] = __expf(s[i] - mx); sum += s[i]; }
-  const float inv = 1.f / sum;
-  p.lse[((long long)b * p.heads + h) * 128 + tid] = mx + logf(sum);
+  for (int i = 0; i < 64; ++i) { s[i] = __expf(s[i] - mx_safe); sum += s[i]; }
+  sRed[tid] = make_float2(mx, sum);
+  __syncthreads();
+  const float2 other = sRed[tid ^ 128];
+  const float m_all = fmaxf(mx, other.x);                               // finite: key 0 is always valid or masked with -10000
+  const float mine = mx == -INFINITY ? 0.f : __expf(mx - m_all), theirs = other.x == -INFINITY ? 0.f : __expf(other.x - m_all);
+  const float total = sum * mine + other.y * theirs;
+  const float inv = mine / total;
+  if (ch == 0) p.lse[((long long)b * p.heads + h) * 128 + row] = m_all + logf(total);
   if (p.p_drop > 0.f && p.seed) {
-    uint32_t keep[4];
-    attn_keep_bits(*p.seed, p.site, (uint32_t)((b * p.heads + h) * 128 + tid), dropout_threshold(p.p_drop), keep);
+    uint32_t keep[2];
+    attn_keep_half(*p.seed, p.site, (uint32_t)((b * p.heads + h) * 128 + row), dropout_threshold(p.p_drop), ch, keep);
     const float invk = inv / (1.f - p.p_drop);
 #pragma unroll
-    for (int i = 0; i < 128; ++i) s[i] = ((keep[i >> 5] >> (i & 31)) & 1u) ? s[i] * invk : 0.f;
+    for (int i = 0; i < 64; ++i) s[i] = ((keep[i >> 5] >> (i & 31)) & 1u) ? s[i] * invk : 0.f;
   } else {
 #pragma unroll
-    for (int i = 0; i < 128; ++i) s[i] *= inv;
+    for (int i = 0; i < 64; ++i) s[i] *= inv;
   }
-  store_row_bf16(sP, tid, s);
+  store_half_row_bf16(sP + ch * ATT_CHUNK, row, s);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -181,7 +191,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   mbar_wait(&bars[1], 1);
   __syncwarp();
   tc_fence_after();
-  store_tmem_rows<D>(trow + 128, p.out + ((long long)b * p.sq + tid) * p.ldo + h * D, tid < p.sq);
+  store_tmem_cols<D / 64>(trow + 128 + ch * (D / 2), p.out + ((long long)b * p.sq + row) * p.ldo + h * D + ch * (D / 2), row < p.sq);
 
   tc_fence_before();
   __syncthreads();
@@ -189,7 +199,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 template <int D>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                 const AttnKernelParams p) {
@@ -204,10 +214,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sP = sdO + NC * ATT_CHUNK;
   uint8_t* sdS = sP + 2 * ATT_CHUNK;
   float* sBias = reinterpret_cast<float*>(sdS + 2 * ATT_CHUNK);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 128);
+  float2* sRed = reinterpret_cast<float2*>(sBias + 128);          // [256]: .x = partial sum_k P dP of every half row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRed + ATT_THREADS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, ch = tid >> 7;
   const int h = blockIdx.x, b = blockIdx.y;
 
   if (tid == 0) {
@@ -217,7 +229,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.sk + tid] : 0.f) : -INFINITY;
+  if (tid < 128) sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.sk + tid] : 0.f) : -INFINITY;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -253,48 +265,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncwarp();
   tc_fence_after();
 
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   const bool drop = p.p_drop > 0.f && p.seed;
-  uint32_t keep[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-  if (drop) attn_keep_bits(*p.seed, p.site, (uint32_t)((b * p.heads + h) * 128 + tid), dropout_threshold(p.p_drop), keep);
+  uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+  if (drop) attn_keep_half(*p.seed, p.site, (uint32_t)((b * p.heads + h) * 128 + row), dropout_threshold(p.p_drop), ch, keep);
   const float invk = drop ? 1.f / (1.f - p.p_drop) : 1.f;
-  const float lse = p.lse[((long long)b * p.heads + h) * 128 + tid];
+  const float lse = p.lse[((long long)b * p.heads + h) * 128 + row];
 
-  float pr[128];
-  tmem_ld_row128(trow, pr);
+  float pr[64];
+  tmem_ld_row64(trow + ch * 64, pr);
 #pragma unroll
-  for (int i = 0; i < 128; ++i) pr[i] = __expf(pr[i] * p.scale + sBias[i] - lse);
+  for (int i = 0; i < 64; ++i) pr[i] = __expf(pr[i] * p.scale + sBias[ch * 64 + i] - lse);
   {
     // P after dropout feeds dV = P_drop^T dO
-    float pd[128];
+    float pd[64];
 #pragma unroll
-    for (int i = 0; i < 128; ++i) pd[i] = ((keep[i >> 5] >> (i & 31)) & 1u) ? pr[i] * invk : 0.f;
-    store_row_bf16(sP, tid, pd);
+    for (int i = 0; i < 64; ++i) pd[i] = ((keep[i >> 5] >> (i & 31)) & 1u) ? pr[i] * invk : 0.f;
+    store_half_row_bf16(sP + ch * ATT_CHUNK, row, pd);
   }
-  float drow = 0.f;
+  float dp[64];
+  tmem_ld_row64(trow + 128 + ch * 64, dp);
+  float part = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(trow + 128 + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float dp = ((keep[c] >> i) & 1u) ? __uint_as_float(r[i]) * invk : 0.f;
-      drow += pr[c * 32 + i] * dp;
-    }
+  for (int i = 0; i < 64; ++i) {
+    dp[i] = ((keep[i >> 5] >> (i & 31)) & 1u) ? dp[i] * invk : 0.f;
+    part += pr[i] * dp[i];
   }
+  sRed[tid] = make_float2(part, 0.f);
+  __syncthreads();
+  const float drow = part + sRed[tid ^ 128].x;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t r[32];
-    tmem_ld_32x32(trow + 128 + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float dp = ((keep[c] >> i) & 1u) ? __uint_as_float(r[i]) * invk : 0.f;
-      pr[c * 32 + i] = pr[c * 32 + i] * (dp - drow) * p.scale;   // dS (scaled so that dQ = dS K, dK = dS^T Q)
-    }
-  }
-  store_row_bf16(sdS, tid, pr);
+  for (int i = 0; i < 64; ++i) pr[i] = pr[i] * (dp[i] - drow) * p.scale;   // dS (scaled so that dQ = dS K, dK = dS^T Q)
+  store_half_row_bf16(sdS + ch * ATT_CHUNK, row, pr);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -318,9 +320,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   mbar_wait(&bars[1], 1);
   __syncwarp();
   tc_fence_after();
-  store_tmem_rows<D>(trow, p.dq + ((long long)b * p.sq + tid) * p.lddq + h * D, tid < p.sq);
-  store_tmem_rows<D>(trow + 256, p.dv + ((long long)b * p.sk + tid) * p.lddv + h * D, tid < p.sk);
-  store_tmem_rows<D>(trow + 384, p.dk + ((long long)b * p.sk + tid) * p.lddk + h * D, tid < p.sk);
+  constexpr int HD = D / 2;   // each of the two threads of a row stores half of the head width
+  store_tmem_cols<D / 64>(trow + ch * HD, p.dq + ((long long)b * p.sq + row) * p.lddq + h * D + ch * HD, row < p.sq);
+  store_tmem_cols<D / 64>(trow + 256 + ch * HD, p.dv + ((long long)b * p.sk + row) * p.lddv + h * D + ch * HD, row < p.sk);
+  store_tmem_cols<D / 64>(trow + 384 + ch * HD, p.dk + ((long long)b * p.sk + row) * p.lddk + h * D + ch * HD, row < p.sk);
 
   tc_fence_before();
   __syncthreads();
@@ -329,7 +332,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 template <int D>
 static constexpr int attn_smem_bytes(bool bwd) {
-  return (bwd ? 4 : 3) * (D / 64) * ATT_CHUNK + (bwd ? 4 : 2) * ATT_CHUNK + 128 * 4 + 64 + 1024;
+  return (bwd ? 4 : 3) * (D / 64) * ATT_CHUNK + (bwd ? 4 : 2) * ATT_CHUNK + 128 * 4 + ATT_THREADS * 8 + 64 + 1024;
 }
 
 static int make_view_map(CUtensorMap* m, const void* base, int width, int seq, int batch, long long ld) {
@@ -358,7 +361,7 @@ static int launch_attn(const vb_attn_args& a, bool bwd, cudaStream_t stream) {
       VB_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<D>(false)));
       attr = true;
     }
-    attn_fwd_kernel<D><<<grid, 128, attn_smem_bytes<D>(false), stream>>>(mq, mk, mv, p);
+    attn_fwd_kernel<D><<<grid, ATT_THREADS, attn_smem_bytes<D>(false), stream>>>(mq, mk, mv, p);
   } else {
     if ((rc = make_view_map(&mdo, a.dout, width, a.sq, a.batch, a.lddo)) != VB_OK) return rc;
     static bool attr = false;
@@ -366,7 +369,7 @@ static int launch_attn(const vb_attn_args& a, bool bwd, cudaStream_t stream) {
       VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<D>(true)));
       attr = true;
     }
-    attn_bwd_kernel<D><<<grid, 128, attn_smem_bytes<D>(true), stream>>>(mq, mk, mv, mdo, p);
+    attn_bwd_kernel<D><<<grid, ATT_THREADS, attn_smem_bytes<D>(true), stream>>>(mq, mk, mv, mdo, p);
   }
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;

@@ -37,6 +37,9 @@ constexpr int LN_WARPS = 8;
 struct LnParams {
   const __nv_bfloat16* x;     // [M,H] dense output (pre-dropout)
   const __nv_bfloat16* res;   // [M,H] residual or null
+  const float* res32;         // the same residual in fp32 (takes precedence): the residual stream is carried in fp32
+  float* y32;                 // optional fp32 copy of the output (the next block's residual)
+  long long ldres32, ldy32;
   const float* gamma;
   const float* beta;
   __nv_bfloat16* y;           // fwd out
@@ -78,7 +81,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[j][i] = k[i] ? v[j][i] * inv_in : 0.f;
       }
-      if (p.res) {
+      if (p.res32) {
+        float r[8];
+        ld8f(p.res32 + (long long)row * p.ldres32 + col, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] += r[i];
+      } else if (p.res) {
         float r[8];
         ld8(p.res + (long long)row * p.ldres + col, r);
 #pragma unroll
@@ -109,6 +117,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const LnParams p)
         for (int i = 0; i < 8; ++i) o[i] = k[i] ? o[i] * inv_out : 0.f;
       }
       st8(p.y + (long long)row * p.ldy + col, o);
+      if (p.y32) {
+        float* o32 = p.y32 + (long long)row * p.ldy32 + col;
+        *reinterpret_cast<float4*>(o32) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(o32 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
     }
     if (lane == 0) {
       if (p.mean) p.mean[row] = mean;
@@ -161,7 +174,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnParams p)
       const int col = (lane + 32 * j) * 8;
       xr[j] = *reinterpret_cast<const uint4*>(p.x + (long long)row * p.ldx + col);
       dr[j] = *reinterpret_cast<const uint4*>(p.dy + (long long)row * p.lddy + col);
-      if (p.res) rr[j] = *reinterpret_cast<const uint4*>(p.res + (long long)row * p.ldres + col);
+      if (p.res && !p.res32) rr[j] = *reinterpret_cast<const uint4*>(p.res + (long long)row * p.ldres + col);
     }
     const float mean = p.mean[row], rstd = p.rstd[row];
     float xh[NV][8], dxh[NV][8];
@@ -183,7 +196,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const LnParams p)
 #pragma unroll
         for (int i = 0; i < 8; ++i) { v[i] = k[i] ? v[i] * inv_in : 0.f; keep_in[j] |= (k[i] ? 1u : 0u) << i; }
       }
-      if (p.res) {
+      if (p.res32) {
+        float r[8];
+        ld8f(p.res32 + (long long)row * p.ldres32 + col, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += r[i];
+      } else if (p.res) {
         const float2 a = unpack_bf16x2(rr[j].x), b = unpack_bf16x2(rr[j].y), c = unpack_bf16x2(rr[j].z), e = unpack_bf16x2(rr[j].w);
         v[0] += a.x; v[1] += a.y; v[2] += b.x; v[3] += b.y; v[4] += c.x; v[5] += c.y; v[6] += e.x; v[7] += e.y;
       }
@@ -253,6 +271,7 @@ struct EmbParams {
   const float* gamma;
   const float* beta;
   __nv_bfloat16* y;      // [B*T,H]
+  float* y32;            // optional fp32 copy (residual stream)
   float* mean;
   float* rstd;
   const __nv_bfloat16* dy;
@@ -307,6 +326,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) emb_fwd_kernel(const EmbParams 
         for (int i = 0; i < 8; ++i) o[i] = k[i] ? o[i] * inv_out : 0.f;
       }
       st8(p.y + (long long)row * p.h + col, o);
+      if (p.y32) {
+        float* o32 = p.y32 + (long long)row * p.h + col;
+        *reinterpret_cast<float4*>(o32) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(o32 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
     }
     if (lane == 0) { p.mean[row] = mean; p.rstd[row] = rstd; }
   }
@@ -629,6 +653,8 @@ static int fill_ln(LnParams& p, const vb_layernorm_args* a) {
   VB_REQUIRE((a->p_in == 0.f && a->p_out == 0.f) || a->seed != nullptr, "dropout needs a device seed pointer");
   p.x = (const __nv_bfloat16*)a->x; p.res = (const __nv_bfloat16*)a->res; p.gamma = a->gamma; p.beta = a->beta;
   p.y = (__nv_bfloat16*)a->y; p.mean = a->mean; p.rstd = a->rstd;
+  p.res32 = a->res_f32; p.y32 = a->y_f32; p.ldres32 = a->ldres_f32; p.ldy32 = a->ldy_f32;
+  VB_REQUIRE(aligned16(a->res_f32) && aligned16(a->y_f32) && a->ldres_f32 % 4 == 0 && a->ldy_f32 % 4 == 0, "fp32 residual / output alignment");
   p.dy = (const __nv_bfloat16*)a->dy; p.dx = (__nv_bfloat16*)a->dx; p.dres = (__nv_bfloat16*)a->dres;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
   p.ldx = a->ldx; p.ldres = a->ldres; p.ldy = a->ldy; p.lddy = a->lddy; p.lddx = a->lddx; p.lddres = a->lddres;
@@ -683,7 +709,7 @@ static int fill_emb(EmbParams& p, const vb_embed_args* a) {
   VB_REQUIRE(a->b > 0 && a->t > 0 && a->h % 256 == 0, "h must be a multiple of 256");
   VB_REQUIRE(a->p_out == 0.f || a->seed != nullptr, "dropout needs a device seed pointer");
   p.ids = a->ids; p.type_ids = a->type_ids; p.word = a->word; p.pos = a->pos; p.type = a->type;
-  p.gamma = a->gamma; p.beta = a->beta; p.y = (__nv_bfloat16*)a->y; p.mean = a->mean; p.rstd = a->rstd;
+  p.gamma = a->gamma; p.beta = a->beta; p.y = (__nv_bfloat16*)a->y; p.y32 = a->y_f32; p.mean = a->mean; p.rstd = a->rstd;
   p.dy = (const __nv_bfloat16*)a->dy; p.dword = a->dword; p.dpos = a->dpos; p.dtype = a->dtype;
   p.dgamma = a->dgamma; p.dbeta = a->dbeta;
   p.b = a->b; p.t = a->t; p.h = a->h; p.vocab = a->vocab; p.eps = a->eps; p.p_out = a->p_out; p.site_out = a->site_out;

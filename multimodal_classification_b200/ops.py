@@ -77,8 +77,8 @@ def _ld(t):
     return 0 if t is None else t.stride(0)
 
 
-def _ln_args(x, res, gamma, beta, mean, rstd, eps, p_in, site_in, p_out, site_out, seed):
-    _need_cuda(x, res, gamma, beta, mean, rstd, seed)
+def _ln_args(x, res, gamma, beta, mean, rstd, eps, p_in, site_in, p_out, site_out, seed, res32=None):
+    _need_cuda(x, res, gamma, beta, mean, rstd, seed, res32)
     m, h = x.shape
     assert x.dtype == torch.bfloat16 and x.stride(1) == 1
     a = _lib.LayerNormArgs()
@@ -88,24 +88,30 @@ def _ln_args(x, res, gamma, beta, mean, rstd, eps, p_in, site_in, p_out, site_ou
     a.m, a.h, a.eps = m, h, eps
     a.p_in, a.p_out, a.site_in, a.site_out = p_in, p_out, site_in, site_out
     a.seed = _ptr(seed)
+    if res32 is not None:
+        assert res32.dtype == torch.float32 and res32.shape == x.shape and res32.stride(1) == 1
+        a.res_f32, a.ldres_f32 = res32.data_ptr(), res32.stride(0)
     return a
 
 
 def layernorm_fwd(x, res, gamma, beta, y, mean, rstd, *, eps=1e-12, p_in=0.0, site_in=0, p_out=0.0, site_out=0,
-                  seed=None):
+                  seed=None, res32=None, y32=None):
     """y = dropout_out(LN(dropout_in(x) + res)); BertLayerNorm + the dropout / residual before it
     (reference models/vilbert_facebook_arch.py:63-76, 156-160, 197-201, 329-336)."""
-    a = _ln_args(x, res, gamma, beta, mean, rstd, eps, p_in, site_in, p_out, site_out, seed)
-    _need_cuda(y)
+    a = _ln_args(x, res, gamma, beta, mean, rstd, eps, p_in, site_in, p_out, site_out, seed, res32)
+    _need_cuda(y, y32)
     a.y, a.ldy = y.data_ptr(), y.stride(0)
+    if y32 is not None:
+        assert y32.dtype == torch.float32 and y32.shape == x.shape and y32.stride(1) == 1
+        a.y_f32, a.ldy_f32 = y32.data_ptr(), y32.stride(0)
     _lib.check(_lib.lib().vb_layernorm_fwd(C.byref(a), _stream()), "vb_layernorm_fwd")
     return y
 
 
 def layernorm_bwd(dy, x, res, gamma, mean, rstd, *, dx=None, dres=None, dgamma=None, dbeta=None, dbias=None,
-                  eps=1e-12, p_in=0.0, site_in=0, p_out=0.0, site_out=0, seed=None):
+                  eps=1e-12, p_in=0.0, site_in=0, p_out=0.0, site_out=0, seed=None, res32=None):
     """Gradients of layernorm_fwd; dgamma / dbeta / dbias are accumulated atomically (zero them first)."""
-    a = _ln_args(x, res, gamma, None, mean, rstd, eps, p_in, site_in, p_out, site_out, seed)
+    a = _ln_args(x, res, gamma, None, mean, rstd, eps, p_in, site_in, p_out, site_out, seed, res32)
     _need_cuda(dy, dx, dres, dgamma, dbeta, dbias)
     a.dy, a.lddy = dy.data_ptr(), dy.stride(0)
     a.dx, a.lddx, a.dres, a.lddres = _ptr(dx), _ld(dx), _ptr(dres), _ld(dres)
@@ -127,10 +133,13 @@ def _emb_args(ids, type_ids, word, pos, typ, gamma, beta, mean, rstd, b, t, eps,
 
 
 def embed_text_fwd(ids, type_ids, word, pos, typ, gamma, beta, y, mean, rstd, b, t, *, eps=1e-12, p_out=0.0,
-                   site_out=0, seed=None):
+                   site_out=0, seed=None, y32=None):
     """transformers BertEmbeddings.forward as called at models/vilbert_facebook_arch.py:524."""
     a = _emb_args(ids, type_ids, word, pos, typ, gamma, beta, mean, rstd, b, t, eps, p_out, site_out, seed)
     a.y = y.data_ptr()
+    if y32 is not None:
+        assert y32.dtype == torch.float32 and y32.is_contiguous() and y32.shape == y.shape
+        a.y_f32 = y32.data_ptr()
     _lib.check(_lib.lib().vb_embed_text_fwd(C.byref(a), _stream()), "vb_embed_text_fwd")
     return y
 
