@@ -89,7 +89,7 @@ __device__ __forceinline__ void attn_keep_half(uint64_t seed, uint32_t site, uin
 }
 
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, D == 64 ? 2 : 1)   // 64-wide heads: 84 KB smem, 256 TMEM columns, <= 128 registers -> two CTAs per SM
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const AttnKernelParams p) {
   constexpr int NC = D / 64;
