@@ -12,11 +12,6 @@
 
 namespace vb {
 
-#ifndef VB_SPIN_LIMIT
-// every mbarrier wait is bounded: a broken pipeline traps instead of hanging the GPU box.
-#define VB_SPIN_LIMIT (1u << 26)
-#endif
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
