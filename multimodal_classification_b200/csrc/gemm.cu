@@ -749,6 +749,8 @@ static double tile_cost(int bn, int cg, int np, int kb, double ctas, bool f32_ou
 }
 
 static bool tile_legal(const vb_gemm_args& a, int bn, int cg) {
+  static const int max_bn = getenv("VB_GEMM_MAX_BN") ? atoi(getenv("VB_GEMM_MAX_BN")) : 256;   // experiments: compact tiles only
+  if (bn > max_bn) return false;
   if (cg == 1) return bn == 64 || bn == 128;
   if (a.b_mn_major) return bn == 128 || bn == 256;              // 64-wide MN pieces per CTA
   if (a.a_mn_major) return bn == 128;                           // (MN, K): API completeness only
