@@ -176,6 +176,56 @@ def gemm_kernel_roofline(torch, peaks):
             "frac_of_burst_peak": 2.0 * m * n * k / dt / 1e12 / peaks["bf16_burst"]}
 
 
+def time_ingest(torch, dev, step, timed, steps):
+    """Train samples/s with every batch coming through multimodal_classification_b200.ingest.FeatureStoreLoader from host
+    records (lmdb_dataset.py-shaped pickles held in a dict standing in for detectron.lmdb), loss read back every step."""
+    import pickle
+    import numpy as np
+    import pandas as pd
+    from multimodal_classification_b200 import ingest
+    rng = np.random.default_rng(1234)
+    n_rec = 64
+    store = {}
+    for i in range(n_rec):
+        x1, y1 = rng.uniform(0, 700, R), rng.uniform(0, 700, R)
+        boxes = np.stack([x1, y1, x1 + rng.uniform(50, 300, R), y1 + rng.uniform(50, 300, R)], 1).astype(np.float32)
+        store[str(i).encode()] = pickle.dumps({"features": np.abs(rng.standard_normal((R, 2048))).astype(np.float32),
+                                               "boxes": boxes}, protocol=4)
+
+    class SyntheticTokenizer:      # no vocabulary file offline: seeded ids with ragged lengths, padded like the real one
+        def __call__(self, texts, max_length, **kw):
+            n = len(texts)
+            lens = rng.integers(8, max_length + 1, n)
+            mask = (np.arange(max_length)[None, :] < lens[:, None]).astype(np.int64)
+            return {"input_ids": rng.integers(1, 30522, (n, max_length)) * mask, "attention_mask": mask,
+                    "token_type_ids": np.zeros((n, max_length), np.int64)}
+
+    rows = (steps + 6) * B
+    df = pd.DataFrame({"id": [i % n_rec for i in range(rows)], "text": ["synthetic"] * rows,
+                       "label": rng.integers(0, 2, rows).tolist()})
+    loader = ingest.FeatureStoreLoader(df, ingest.LMDBRecords(store.get, R, 2048), SyntheticTokenizer(), T, B, drop_last=True,
+                                       device=dev)
+    # producer alone: decode + pack + H2D + unpack, no model
+    t0 = time.perf_counter()
+    n = 0
+    for batch in loader:
+        n += batch["labels"].shape[0]
+    torch.cuda.synchronize()
+    loader_only = n / (time.perf_counter() - t0)
+    it = iter(loader)
+
+    def ingest_step():
+        return step(next(it)).item()
+    for _ in range(3):
+        ingest_step()
+    ms = timed(ingest_step, steps)
+    blob = loader._layout(B).nbytes
+    del it
+    return {"value": B / (ms / steps * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "h2d_bytes_per_step": int(blob), "d2h_bytes_per_step": 4, "loader_only_samples_per_sec": loader_only,
+            "source": f"{n_rec} pickled records ({R}x2048 fp32 features + {R}x4 boxes) in host memory, 1 producer thread, ring of 3"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -291,6 +341,15 @@ def main():
         opt_step()
     ms_opt = timed(opt_step, args.steps)
 
+    # ---- the same step fed by the feature-store loader: records decoded from an in-memory LMDB image
+    #      by the producer thread, one pinned blob + one H2D + one unpack launch per batch, overlapped with the previous step
+    ingest = None
+    if world == 1:
+        try:
+            ingest = time_ingest(torch, dev, step, timed, max(args.steps, 60))
+        except Exception as e:      # the headline line must still print
+            ingest = {"error": repr(e)[:200]}
+
     if rank == 0:
         step_tflops = FLOP_PER_SAMPLE_FWD_BWD * value / world / 1e12      # per GPU
         dom = gemm_kernel_roofline(torch, peaks)
@@ -316,6 +375,8 @@ def main():
                 "with_fused_optimizer": {"value": world * B / (ms_opt / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_opt / args.steps,
                                          "step": "fwd+bwd + fused clip/AdamW/bf16-shadow pass (2 launches)"},
                 "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "roofline": roofline, "clocks": clocks}
+        if ingest is not None:
+            line["ingest"] = ingest
         if world == 1 and not args.no_cpu_baseline:
             v, cores, n = time_cpu_port(25.0, B)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -259,6 +259,19 @@ int vb_bilinear_concat(const float* const* layers, int32_t num_layers, void* out
 int vb_gelu_bf16(const void* x, void* y, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Feature-store ingest (next-row f-3; pipelines/data_processing/lmdb_dataset.py:143-208).
+ *   vb_lmdb_regions : one batch of detectron.lmdb records, already in HBM as raw fp32 arrays, becomes what the encoder
+ *                     consumes.  features fp32 [n_features] (= rows * feature_dim, multiple of 8) -> features_bf16
+ *                     (round-to-nearest-even, the A operand of `image_embeddings`); boxes fp32 [rows, box_stride >= 4]
+ *                     (x1, y1, x2, y2, ...) -> spatial fp32 [rows, 5] = [x1/box_div, y1/box_div, x2/box_div, y2/box_div,
+ *                     ((x2-x1)*(y2-y1))/area_div], the float32 operation order of `_process_boxes` (:189-208; box_div
+ *                     1000, area_div 1e6), bit-exact.  rows = 0 skips the boxes (HDF5-layout stores keep final spatial
+ *                     rows, precomputed_dataset.py:90-92); n_features = 0 skips the cast.  One launch.
+ * ---------------------------------------------------------------------------------------------- */
+int vb_lmdb_regions(const float* features, void* features_bf16, int64_t n_features, const float* boxes, float* spatial,
+                    int32_t rows, int32_t box_stride, float box_div, float area_div, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused optimizer step over the flat parameter / gradient buffers (next-row f-1 of SURVEY.md §8): replaces
  * torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step() of pipelines/model_training/nodes.py:795-799.
  *   vb_grad_sumsq : *acc += sum(grad[i]^2)  (fp64 device accumulator, zero it first; call once per contiguous range)

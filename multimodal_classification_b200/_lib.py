@@ -132,6 +132,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_adamw_step": [C.POINTER(AdamWArgs), vp],
         "vb_box_area_score": [vp, i32, f32, f32, f32, vp, vp],
         "vb_nms": [vp, vp, i32, f32, vp, vp, vp, vp],
+        "vb_lmdb_regions": [vp, vp, i64, vp, vp, i32, i32, f32, f32, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)

@@ -407,3 +407,24 @@ def nms(boxes, scores, iou_threshold):
     _lib.check(_lib.lib().vb_nms(boxes.data_ptr(), scores.data_ptr(), n, float(iou_threshold), ws.data_ptr(), keep.data_ptr(),
                                  cnt.data_ptr(), _stream()), "vb_nms")
     return keep[:int(cnt.item())].long()
+
+
+def lmdb_regions(features=None, features_bf16=None, boxes=None, spatial=None, box_div=1000.0, area_div=1000000.0, stream=None):
+    """Raw LMDB batch -> encoder inputs in one launch: fp32 features -> bf16; raw boxes [rows, >=4] -> spatial [rows, 5]
+    (lmdb_dataset.py:189-208, bit-exact).  Either half may be omitted."""
+    n = rows = stride = 0
+    if features is not None:
+        _need_cuda(features, features_bf16)
+        assert features.dtype == torch.float32 and features_bf16.dtype == torch.bfloat16
+        assert features.is_contiguous() and features_bf16.is_contiguous() and features.numel() == features_bf16.numel()
+        n = features.numel()
+    if boxes is not None:
+        _need_cuda(boxes, spatial)
+        assert boxes.dtype == torch.float32 and spatial.dtype == torch.float32 and boxes.is_contiguous() and spatial.is_contiguous()
+        stride = boxes.shape[-1]
+        rows = boxes.numel() // stride
+        assert spatial.numel() == rows * 5
+    _lib.check(_lib.lib().vb_lmdb_regions(_ptr(features), _ptr(features_bf16), n, _ptr(boxes), _ptr(spatial), rows, stride,
+                                          float(box_div), float(area_div),
+                                          _stream() if stream is None else stream.cuda_stream), "vb_lmdb_regions")
+    return features_bf16, spatial

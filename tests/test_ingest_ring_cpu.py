@@ -1,0 +1,97 @@
+"""The loader's producer/consumer ring (multimodal_classification_b200/ingest.py) exercised on the CPU: CUDA streams, events
+and pinned memory are replaced by inert stand-ins and the one kernel by the oracle's arithmetic, so that slot hand-over,
+epoch restarts, short last batches, abandoned epochs and producer errors are covered without a GPU.  The real device path
+is tests/test_ingest_gpu.py."""
+import contextlib
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ingest_oracle as io
+
+from ingest_fixture import BS, F, G, KEYS, R, T, frame, golden_batches, store, tokenizer  # noqa: E402
+
+
+class _Event:
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def wait_event(self, event):
+        pass
+
+
+@pytest.fixture
+def ingest_on_cpu(monkeypatch):
+    from multimodal_classification_b200 import ingest, ops
+    if torch.cuda.is_available():
+        pytest.skip("stand-ins are for the GPU-less container")
+    for name, value in [("is_available", lambda: True), ("current_device", lambda: 0), ("set_device", lambda d: None),
+                        ("device", lambda d: contextlib.nullcontext()), ("stream", lambda s: contextlib.nullcontext()),
+                        ("current_stream", lambda d=None: _Stream()), ("Stream", _Stream), ("Event", _Event)]:
+        monkeypatch.setattr(torch.cuda, name, value)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+
+    def regions(features=None, features_bf16=None, boxes=None, spatial=None, box_div=1000.0, area_div=1e6, stream=None):
+        if features is not None:
+            features_bf16.copy_(features.to(torch.bfloat16))
+        if boxes is not None:
+            b = boxes.reshape(-1, boxes.shape[-1]).numpy()
+            spatial.copy_(torch.from_numpy(io.process_boxes(b, b.shape[0])).view(spatial.shape))
+    monkeypatch.setattr(ops, "lmdb_regions", regions)
+    return ingest
+
+
+def check(batch, want, dt):
+    assert list(batch.keys()) == KEYS
+    for k in KEYS:
+        got = batch[k]
+        assert tuple(got.shape) == want[k].shape, k
+        if k == "visual_features" and dt == torch.bfloat16:
+            assert torch.equal(got.view(torch.int16), torch.from_numpy(want[k]).to(torch.bfloat16).view(torch.int16))
+        else:
+            assert got.numpy().dtype == want[k].dtype and np.array_equal(got.numpy(), want[k]), k
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("depth", [2, 3, 5])
+def test_ring_yields_reference_batches_over_epochs(ingest_on_cpu, dt, depth):
+    ingest = ingest_on_cpu
+    rec = ingest.LMDBRecords(store().get, R, F)
+    seq = ingest.FeatureStoreLoader(frame(), rec, tokenizer(), T, BS, depth=depth, feature_dtype=dt, device="cpu")
+    assert len(seq) == 3 and len(seq.dataset) == len(G["ids"])
+    for _ in range(2):
+        assert sum(check(b, w, dt) is None for b, w in zip(seq, golden_batches("lmdb_seq"))) == 3
+    shuf = ingest.FeatureStoreLoader(frame(), rec, tokenizer(), T, BS, shuffle=True, drop_last=True, depth=depth,
+                                     feature_dtype=dt, device="cpu")
+    torch.manual_seed(2024)
+    assert sum(check(b, w, dt) is None for b, w in zip(shuf, golden_batches("lmdb_shuf"))) == len(shuf) == 2
+    id_map = {str(k): int(v) for k, v in zip(G["h5_ids"], G["h5_rows"])}
+    h5 = ingest.FeatureStoreLoader(frame(), ingest.ArrayRecords(G["h5_visual"], G["h5_spatial"], id_map, R, F), tokenizer(), T,
+                                   BS, depth=depth, feature_dtype=dt, device="cpu")
+    assert sum(check(b, w, dt) is None for b, w in zip(h5, golden_batches("h5_seq"))) == 3
+
+
+def test_ring_errors_early_exit_and_empty_split(ingest_on_cpu):
+    ingest = ingest_on_cpu
+    st = store()
+    st[b"1006"] = pickle.dumps({"features": np.zeros((R + 2, F), np.float32)})
+    with pytest.raises(ingest.VbError, match="features of shape"):
+        list(ingest.FeatureStoreLoader(frame(), ingest.LMDBRecords(st.get, R, F), tokenizer(), T, BS, device="cpu"))
+    good = ingest.FeatureStoreLoader(frame(), ingest.LMDBRecords(store().get, R, F), tokenizer(), T, 2, device="cpu")
+    for i, _ in enumerate(good):
+        if i == 1:
+            break
+    assert len(list(good)) == len(good) == 6
+    empty = ingest.FeatureStoreLoader(frame().iloc[:0], ingest.LMDBRecords(store().get, R, F), tokenizer(), T, 2, device="cpu")
+    assert len(empty) == 0 and list(empty) == []
+    with pytest.raises(ingest.VbError):
+        ingest.FeatureStoreLoader(frame(), ingest.LMDBRecords(store().get, R, F), tokenizer(), T, 2, device="cpu", depth=1)
