@@ -176,7 +176,7 @@ def gemm_kernel_roofline(torch, peaks):
             "frac_of_burst_peak": 2.0 * m * n * k / dt / 1e12 / peaks["bf16_burst"]}
 
 
-def time_ingest(torch, dev, step, timed, steps):
+def time_ingest(torch, dev, step, timed, steps, **loader_kw):
     """Train samples/s with every batch coming through multimodal_classification_b200.ingest.FeatureStoreLoader from host
     records (lmdb_dataset.py-shaped pickles held in a dict standing in for detectron.lmdb), loss read back every step."""
     import pickle
@@ -204,7 +204,7 @@ def time_ingest(torch, dev, step, timed, steps):
     df = pd.DataFrame({"id": [i % n_rec for i in range(rows)], "text": ["synthetic"] * rows,
                        "label": rng.integers(0, 2, rows).tolist()})
     loader = ingest.FeatureStoreLoader(df, ingest.LMDBRecords(store.get, R, 2048), SyntheticTokenizer(), T, B, drop_last=True,
-                                       device=dev)
+                                       device=dev, **loader_kw)
     # producer alone: decode + pack + H2D + unpack, no model
     t0 = time.perf_counter()
     n = 0

@@ -3,11 +3,13 @@ reference's Kedro nodes run; no reference file is edited.
 
 The reference resolves the model inside ``_load_facebook_model`` (pipelines/model_training/nodes.py:223-230) from
 ``multimodalclassification.models`` and the extractor through the dict literal in
-``models/feature_extractors/__init__.py:101-112`` / ``FEATURE_EXTRACTOR_REGISTRY`` (models/base.py:274)."""
+``models/feature_extractors/__init__.py:101-112`` / ``FEATURE_EXTRACTOR_REGISTRY`` (models/base.py:274), and the feature-store
+loaders inside ``create_dataloaders_lmdb / create_dataloaders_precomputed`` (nodes.py:605-658) from
+``pipelines.data_processing.lmdb_dataset / precomputed_dataset``."""
 from __future__ import annotations
 
 
-def install() -> None:
+def install(ingest: bool = True) -> None:
     import multimodalclassification.models as M
     import multimodalclassification.models.base as B
     import multimodalclassification.models.feature_extractors as FE
@@ -21,3 +23,11 @@ def install() -> None:
     M.load_facebook_weights = A.load_facebook_weights = load_facebook_weights
     FE.ResNet152ROIExtractor = ResNet152ROIExtractor
     B.FEATURE_EXTRACTOR_REGISTRY["resnet152_roi"] = ResNet152ROIExtractor
+    if ingest:
+        from . import ingest as I
+        for module, name in (("lmdb_dataset", "create_lmdb_dataloaders"), ("precomputed_dataset", "create_precomputed_dataloaders")):
+            try:        # these modules import lmdb / h5py / kedro; where those are absent the pipelines cannot run at all
+                mod = __import__("multimodalclassification.pipelines.data_processing." + module, fromlist=[name])
+            except ImportError:
+                continue
+            setattr(mod, name, getattr(I, name))

@@ -21,6 +21,7 @@ from __future__ import annotations
 import pickle
 import queue
 import threading
+import time
 from typing import Callable, Dict, Iterator, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -214,6 +215,21 @@ class _Slot:
         self.ready = torch.cuda.Event()
         self.released = torch.cuda.Event()
         self.released.record()
+        self._views: Dict[int, tuple] = {}
+
+    def views(self, lay: BatchLayout, boxes_are_raw: bool):
+        """(numpy views of the pinned blob, torch views of the HBM blob, the batch dict handed to the consumer), cached per
+        batch size so that neither thread builds tensor views in steady state."""
+        got = self._views.get(lay.batch)
+        if got is None:
+            host = {k: v.numpy() for k, v in lay.views(self.host).items()}
+            dev, b = lay.views(self.dev), lay.batch
+            batch = {"input_ids": dev["input_ids"], "attention_mask": dev["attention_mask"],
+                     "token_type_ids": dev["token_type_ids"],
+                     "visual_features": self.feat16[:b] if self.feat16 is not None else dev["features"],
+                     "spatial_locations": self.spatial[:b] if boxes_are_raw else dev["boxes"], "labels": dev["labels"]}
+            got = self._views[lay.batch] = (host, dev, batch)
+        return got
 
 
 class FeatureStoreLoader:
@@ -223,7 +239,8 @@ class FeatureStoreLoader:
     bit-identical to the reference loader's (the encoder then rounds them itself — same result)."""
 
     def __init__(self, data, records, tokenizer, max_seq_length: int = 128, batch_size: int = 32, shuffle: bool = False,
-                 drop_last: bool = False, device="cuda", depth: int = 3, feature_dtype: torch.dtype = torch.bfloat16):
+                 drop_last: bool = False, device="cuda", depth: int = 3, feature_dtype: torch.dtype = torch.bfloat16,
+                 start_delay_ms: float = 1.0):
         if not torch.cuda.is_available():
             raise VbError("FeatureStoreLoader stages batches in HBM and needs a CUDA device; there is no CPU fall-back")
         if depth < 2:
@@ -233,7 +250,7 @@ class FeatureStoreLoader:
         self.dataset = TextTable(data, tokenizer, max_seq_length)
         self.records, self.batch_size, self.shuffle, self.drop_last = records, batch_size, shuffle, drop_last
         self.device = torch.device(device if str(device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
-        self.depth, self.feature_dtype = depth, feature_dtype
+        self.depth, self.feature_dtype, self.start_delay = depth, feature_dtype, start_delay_ms * 1e-3
         self._layouts: Dict[int, BatchLayout] = {}
         with torch.cuda.device(self.device):
             self._stream = torch.cuda.Stream()
@@ -257,18 +274,22 @@ class FeatureStoreLoader:
         try:
             torch.cuda.set_device(self.device)
             for indices in plan:
-                slot_id = free.get()
+                try:
+                    slot_id = free.get_nowait()
+                except queue.Empty:
+                    slot_id = free.get()                          # woken by the consumer asking for its next batch:
+                    if self.start_delay > 0:                      # stay off the GIL while it launches that step
+                        time.sleep(self.start_delay)
                 if stop.is_set() or slot_id is None:
                     return
                 slot = self._slots[slot_id]
                 slot.released.synchronize()                       # the consumer's work on this slot's last batch is done
                 slot.ready.synchronize()                          # ... and so is its copy, had the epoch been abandoned
                 lay = self._layout(len(indices))
-                host = {k: v.numpy() for k, v in lay.views(slot.host).items()}
+                host, dev, _ = slot.views(lay, self.records.boxes_are_raw)
                 pack_batch(self.dataset, self.records, indices, host)
                 with torch.cuda.stream(self._stream):
                     slot.dev[:lay.nbytes].copy_(slot.host[:lay.nbytes], non_blocking=True)
-                    dev = lay.views(slot.dev)
                     raw, b = self.records.boxes_are_raw, lay.batch
                     feat16 = slot.feat16[:b] if slot.feat16 is not None else None
                     if feat16 is not None or raw:                 # one launch: bf16 features and/or normalised boxes
@@ -304,12 +325,7 @@ class FeatureStoreLoader:
                 slot = self._slots[slot_id]
                 cur = torch.cuda.current_stream(self.device)
                 cur.wait_event(slot.ready)
-                dev, b = lay.views(slot.dev), lay.batch
-                batch = {"input_ids": dev["input_ids"], "attention_mask": dev["attention_mask"],
-                         "token_type_ids": dev["token_type_ids"],
-                         "visual_features": slot.feat16[:b] if slot.feat16 is not None else dev["features"],
-                         "spatial_locations": slot.spatial[:b] if self.records.boxes_are_raw else dev["boxes"],
-                         "labels": dev["labels"]}
+                batch = dict(slot.views(lay, self.records.boxes_are_raw)[2])
                 held.append(slot_id)
                 if len(held) > max(1, self.depth - 2):             # hand the oldest slot back once its work is enqueued
                     old = held.pop(0)
