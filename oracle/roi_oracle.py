@@ -279,3 +279,24 @@ def seeded_fusion_inputs(seed: int = 21, layers: int = 4, grid: int = 37, hidden
           "projection.3.weight": (torch.rand(out_dim, out_dim, generator=g) * 2 - 1) * math.sqrt(6.0 / (2 * out_dim)),
           "projection.3.bias": (torch.rand(out_dim, generator=g) - 0.5) * 0.1}
     return feats, sd
+
+
+# ------------------------------------------------------------------------------------------------ grid extractor (f-4)
+def grid_backbone_state(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The same weights under the key names of ``ResNetFeatureExtractor.backbone`` (models/feature_extractors/resnet.py:33:
+    ``nn.Sequential(*list(resnet.children())[:-2])`` -> "0." conv1, "1." bn1, "4.".."7." layer1..layer4)."""
+    return {("7." + k[4:] if k.startswith("top.") else k[5:]): v for k, v in sd.items()}
+
+
+def grid_features(sd, img: torch.Tensor, num_regions: int = 36, output_dim: int = 2048) -> np.ndarray:
+    """resnet.py:51-76 on a preprocessed image [1,3,H,W]: whole ResNet-152 trunk, adaptive average pool to a
+    sqrt(num_regions) grid, rows in raster order, zero-padded / truncated to ``output_dim``.  ``sd`` uses the RoI backbone's
+    key names (``seeded_backbone_state``)."""
+    g = int(num_regions ** 0.5)
+    with torch.no_grad():
+        x = _layer(sd, "top", 3, 2, forward_base(sd, img))
+        x = F.adaptive_avg_pool2d(x, (g, g))
+        f = x.view(1, x.shape[1], -1).permute(0, 2, 1).squeeze(0)
+    if f.shape[-1] < output_dim:
+        f = torch.cat([f, torch.zeros(f.shape[0], output_dim - f.shape[-1])], dim=-1)
+    return f[:, :output_dim].numpy()

@@ -37,3 +37,5 @@ def test_install_rebinds_the_reference_lookups():
     # the extractor factory now reaches our class (which refuses a CPU device instead of silently falling back)
     with pytest.raises(VbError):
         get_feature_extractor("resnet152_roi", device="cpu")
+    with pytest.raises(VbError):
+        get_feature_extractor("resnet", device="cpu")
