@@ -16,7 +16,7 @@ def install(ingest: bool = True) -> None:
     import multimodalclassification.models.vilbert_facebook_arch as A
 
     from .resnet152_roi import ResNet152ROIExtractor
-    from .resnet_grid import ResNetFeatureExtractor
+    from .resnet_grid import ResNetFeatureExtractor, ResNetVGExtractor
     from .vilbert import ViLBERTForClassification, get_facebook_vilbert_config, load_facebook_weights
 
     M.ViLBERTFacebookArch = A.ViLBERTForClassification = ViLBERTForClassification
@@ -26,6 +26,8 @@ def install(ingest: bool = True) -> None:
     B.FEATURE_EXTRACTOR_REGISTRY["resnet152_roi"] = ResNet152ROIExtractor
     FE.ResNetFeatureExtractor = ResNetFeatureExtractor                 # "resnet" in the same dict literal / registry
     B.FEATURE_EXTRACTOR_REGISTRY["resnet"] = ResNetFeatureExtractor
+    FE.ResNetVGExtractor = ResNetVGExtractor                           # "resnet_vg"
+    B.FEATURE_EXTRACTOR_REGISTRY["resnet_vg"] = ResNetVGExtractor
     if ingest:
         from . import ingest as I
         for module, name in (("lmdb_dataset", "create_lmdb_dataloaders"), ("precomputed_dataset", "create_precomputed_dataloaders")):

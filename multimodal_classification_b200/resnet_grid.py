@@ -47,10 +47,8 @@ class ResNetFeatureExtractor(nn.Module):
         if not str(device).startswith("cuda"):
             raise VbError("ResNetFeatureExtractor (B200) runs on CUDA only; there is no CPU fallback")
         from torchvision import transforms
-        from torchvision.models import ResNet152_Weights, resnet152
         self.output_dim, self.num_regions, self.device, self.image_size = output_dim, num_regions, device, image_size
-        resnet = resnet152(weights=None if weights is None else getattr(ResNet152_Weights, weights))
-        self.backbone = nn.Sequential(*list(resnet.children())[:-2])           # resnet.py:33 (parameter container only)
+        self.backbone = self._make_backbone(weights)                           # parameter container only
         self.backbone.eval().to(device)
         for p in self.backbone.parameters():
             p.requires_grad = False
@@ -62,16 +60,26 @@ class ResNetFeatureExtractor(nn.Module):
         self._plans: Dict[Tuple[int, int, int], dict] = {}
         self.use_graphs = True
 
+    def _make_backbone(self, weights: Optional[str]) -> nn.Module:
+        from torchvision.models import ResNet152_Weights, resnet152
+        resnet = resnet152(weights=None if weights is None else getattr(ResNet152_Weights, weights))
+        return nn.Sequential(*list(resnet.children())[:-2])                    # resnet.py:33
+
     def _generate_grid_spatial(self, num_regions: Optional[int] = None) -> torch.Tensor:
         """models/base.py:244-270."""
         n = self.num_regions if num_regions is None else num_regions
         g = int(n ** 0.5)
         return grid_spatial(n)[: g * g].to(self.device)
 
+    def _trunk_parts(self) -> Tuple[nn.Sequential, nn.Sequential]:
+        """(conv1 .. layer3 as modules 0..6, layer4) of the parameter container."""
+        return self.backbone, self.backbone[7]
+
     def _get_trunk(self) -> _Trunk:
+        base, top = self._trunk_parts()
         ver = sum(p._version for p in self.backbone.parameters()) + sum(b._version for b in self.backbone.buffers())
-        if self._trunk is None or self._trunk.version != ver or self._trunk.device != self.backbone[0].weight.device:
-            self._trunk = _Trunk(SimpleNamespace(base=self.backbone, top=self.backbone[7]), ver)
+        if self._trunk is None or self._trunk.version != ver or self._trunk.device != base[0].weight.device:
+            self._trunk = _Trunk(SimpleNamespace(base=base, top=top), ver)
         return self._trunk
 
     def _run(self, plan: dict) -> None:
@@ -139,3 +147,62 @@ class ResNetFeatureExtractor(nn.Module):
         """resnet.py:78-85: the same per-image host preprocessing via PIL, then ONE batched pass through the trunk."""
         batch = torch.stack([self.transform(self._to_pil(img.cpu())) for img in images]).to(self.device)
         return self.extract_batch(batch)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the Visual Genome ResNet-101 variant (reference models/feature_extractors/resnet_vg.py)
+# ---------------------------------------------------------------------------------------------------------------------
+class VGResNet101Backbone(nn.Module):
+    """Parameter container with the reference's layout (resnet_vg.py:29-54): ``RCNN_base`` = conv1 .. layer3, ``RCNN_top`` =
+    layer4 of a torchvision ResNet-101 (the Visual Genome Faster R-CNN checkpoint's names)."""
+
+    def __init__(self, weights: Optional[str] = "IMAGENET1K_V1"):
+        super().__init__()
+        from torchvision.models import ResNet101_Weights, resnet101
+        resnet = resnet101(weights=None if weights is None else getattr(ResNet101_Weights, weights))
+        self.RCNN_base = nn.Sequential(resnet.conv1, resnet.bn1, resnet.relu, resnet.maxpool, resnet.layer1, resnet.layer2,
+                                       resnet.layer3)
+        self.RCNN_top = resnet.layer4
+
+
+def load_vg_backbone_weights(model: VGResNet101Backbone, checkpoint_path: str) -> dict:
+    """Same contract as the reference loader (resnet_vg.py:70-120): take ``RCNN_base.*`` / ``RCNN_top.*`` tensors of the
+    checkpoint (``RCNN_top.0.X`` is the model's ``RCNN_top.X``) whose shapes match, ignore everything else, report counts."""
+    checkpoint = torch.load(checkpoint_path, map_location="cpu")
+    state = checkpoint.get("model", checkpoint)
+    own = model.state_dict()
+    loaded, skipped = {}, {}
+    for key, value in state.items():
+        if not (key.startswith("RCNN_base") or key.startswith("RCNN_top")):
+            skipped[key] = "not backbone"
+            continue
+        name = "RCNN_top." + key[len("RCNN_top.0."):] if key.startswith("RCNN_top.0.") else key
+        if name not in own:
+            skipped[key] = "key not in model"
+        elif own[name].shape != value.shape:
+            skipped[key] = f"shape mismatch: {own[name].shape} vs {value.shape}"
+        else:
+            loaded[name] = value
+    model.load_state_dict(loaded, strict=False)
+    return {"loaded": len(loaded), "total_model": len(own), "skipped": len(skipped), "skipped_keys": list(skipped.keys())[:10]}
+
+
+class ResNetVGExtractor(ResNetFeatureExtractor):
+    """Reference ``ResNetVGExtractor`` (resnet_vg.py:123-259): the same grid extraction over the VG-pretrained ResNet-101;
+    ``weights_path`` names the Visual Genome checkpoint, the torchvision weights are kept when it does not exist."""
+
+    def __init__(self, output_dim: int = 2048, num_regions: int = 36, weights_path: Optional[str] = None,
+                 device: Optional[str] = None, *, weights: Optional[str] = "IMAGENET1K_V1", image_size: int = 224):
+        import os
+        super().__init__(output_dim, num_regions, device, weights=weights, image_size=image_size)
+        weights_path = "weights/faster_rcnn_res101_vg.pth" if weights_path is None else weights_path
+        self.has_vg_weights = False
+        if os.path.exists(weights_path):
+            self.has_vg_weights = load_vg_backbone_weights(self.backbone, weights_path)["loaded"] > 0
+        self.grid_size = int(num_regions ** 0.5)
+
+    def _make_backbone(self, weights: Optional[str]) -> nn.Module:
+        return VGResNet101Backbone(weights)
+
+    def _trunk_parts(self) -> Tuple[nn.Sequential, nn.Sequential]:
+        return self.backbone.RCNN_base, self.backbone.RCNN_top

@@ -32,6 +32,25 @@ def main():
     padded, _ = ext.extract_features(Image.fromarray(out["image_u8"]))
     assert padded.shape == (36, 2304) and torch.equal(padded[:, :2048], torch.from_numpy(out["features_36"])) \
         and padded[:, 2048:].abs().max() == 0
+    # the Visual Genome ResNet-101 variant (resnet_vg.py): no checkpoint on disk -> its torchvision-weights branch, then seeded
+    import multimodalclassification.models.feature_extractors.resnet_vg as ref_vg
+    ref_vg.resnet101 = lambda weights=None, **kw: torchvision.models.resnet101(weights=None, **kw)
+    vg = ref_vg.ResNetVGExtractor(weights_path="/nonexistent.pth", device="cpu")
+    print("vg", vg.backbone.load_state_dict(ro.vg_backbone_state(ro.seeded_backbone_state(1, (3, 4, 23, 3))), strict=True))
+    feats, spatial = vg.extract_features(Image.fromarray(out["image_u8"]))
+    out["vg_features_36"] = feats.numpy()[:, ::4].astype(np.float32)
+    out["vg_spatial_36"] = spatial.numpy().astype(np.float32)
+    # ... and its checkpoint loader on a checkpoint with the VG file's key spelling, foreign keys and a wrong shape
+    ck = {("RCNN_top.0." + k[9:] if k.startswith("RCNN_top.") else k): v for k, v in vg.backbone.state_dict().items()}
+    ck["RCNN_rpn.RPN_Conv.weight"] = torch.zeros(4)
+    ck["RCNN_cls_score.weight"] = torch.zeros(4)
+    ck["RCNN_base.0.weight"] = torch.zeros(64, 3, 3, 3)
+    ck["RCNN_base.9.weight"] = torch.zeros(1)
+    torch.save({"model": ck}, "/tmp/_vg_ckpt.pth")
+    fresh = ref_vg.VGResNet101Backbone()
+    stats = ref_vg.load_vg_backbone_weights(fresh, "/tmp/_vg_ckpt.pth")
+    out["vg_loader_stats"] = np.array([stats["loaded"], stats["total_model"], stats["skipped"]])
+    out["vg_loader_skipped_keys"] = np.array(stats["skipped_keys"])
     path = os.path.join(ROOT, "tests", "golden", "resnet_grid.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB; |f| mean %.4f max %.4f" % (np.abs(out["features_36"]).mean(),

@@ -29,8 +29,9 @@ LAYERS = (("base.4", 3, 64, 1), ("base.5", 8, 128, 2), ("base.6", 36, 256, 2), (
 
 
 # ------------------------------------------------------------------------------------------------ seeded weights
-def seeded_backbone_state(seed: int = 0) -> Dict[str, torch.Tensor]:
-    """Deterministic stand-in for the ImageNet checkpoint, keyed like the reference's ``ResNet152Backbone.state_dict()``.
+def seeded_backbone_state(seed: int = 0, blocks: Tuple[int, int, int, int] = (3, 8, 36, 3)) -> Dict[str, torch.Tensor]:
+    """Deterministic stand-in for the ImageNet checkpoint, keyed like the reference's ``ResNet152Backbone.state_dict()``
+    (``blocks`` = bottlenecks per stage: torchvision resnet152 by default, (3, 4, 23, 3) = resnet101).
     He-normal convolutions; BatchNorm statistics and affine parameters drawn so that folding them is not a no-op; the last
     BatchNorm of every bottleneck is damped so that 50 un-normalised residual additions keep activations O(1)."""
     g = torch.Generator().manual_seed(seed)
@@ -49,8 +50,8 @@ def seeded_backbone_state(seed: int = 0) -> Dict[str, torch.Tensor]:
     conv("base.0", 64, 3, 7)
     bn("base.1", 64, 1.0)
     cin = 64
-    for prefix, blocks, width, stride in LAYERS:
-        for b in range(blocks):
+    for (prefix, _, width, stride), nblocks in zip(LAYERS, blocks):
+        for b in range(nblocks):
             p = f"{prefix}.{b}"
             conv(p + ".conv1", width, cin, 1); bn(p + ".bn1", width, 1.0)
             conv(p + ".conv2", width, width, 3); bn(p + ".bn2", width, 1.0)
@@ -78,8 +79,11 @@ def _bottleneck(sd, p, x, stride):
 
 
 def _layer(sd, prefix, blocks, stride, x):
-    for b in range(blocks):
+    """``blocks`` is the torchvision resnet152 count; the count actually present in ``sd`` wins (resnet101 weights)."""
+    b = 0
+    while f"{prefix}.{b}.conv1.weight" in sd:
         x = _bottleneck(sd, f"{prefix}.{b}", x, stride if b == 0 else 1)
+        b += 1
     return x
 
 
@@ -288,8 +292,13 @@ def grid_backbone_state(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return {("7." + k[4:] if k.startswith("top.") else k[5:]): v for k, v in sd.items()}
 
 
+def vg_backbone_state(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The same weights under the key names of ``VGResNet101Backbone`` (models/feature_extractors/resnet_vg.py:29-54)."""
+    return {("RCNN_top." + k[4:] if k.startswith("top.") else "RCNN_base." + k[5:]): v for k, v in sd.items()}
+
+
 def grid_features(sd, img: torch.Tensor, num_regions: int = 36, output_dim: int = 2048) -> np.ndarray:
-    """resnet.py:51-76 on a preprocessed image [1,3,H,W]: whole ResNet-152 trunk, adaptive average pool to a
+    """resnet.py:51-76 (= resnet_vg.py:205-240 with ResNet-101 weights) on a preprocessed image [1,3,H,W]: whole trunk, adaptive average pool to a
     sqrt(num_regions) grid, rows in raster order, zero-padded / truncated to ``output_dim``.  ``sd`` uses the RoI backbone's
     key names (``seeded_backbone_state``)."""
     g = int(num_regions ** 0.5)

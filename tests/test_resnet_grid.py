@@ -107,3 +107,54 @@ def test_grid_batch_padding_and_refusals(extractor):
         extractor.forward(imgs)
     extractor.num_regions = 36
     extractor._plans.clear()
+
+
+# ------------------------------------------------------------------------------------------------ VG ResNet-101 variant
+VG_BLOCKS = (3, 4, 23, 3)
+
+
+def test_oracle_matches_reference_vg_grid_features():
+    got = ro.grid_features(ro.seeded_backbone_state(1, VG_BLOCKS), preprocessed(), 36)[:, ::4]
+    ref = G["vg_features_36"]
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.array_equal(ro.grid_spatial(36), G["vg_spatial_36"])
+
+
+def test_vg_checkpoint_loader_matches_reference_loader(tmp_path):
+    """Same statistics and same resulting weights as the reference's ``load_vg_backbone_weights`` on a checkpoint with the VG
+    file's key spelling (RCNN_top.0.*), foreign keys and one wrong shape (fixture: the reference loader's own report)."""
+    from multimodal_classification_b200.resnet_grid import VGResNet101Backbone, load_vg_backbone_weights
+    seeded = ro.vg_backbone_state(ro.seeded_backbone_state(1, VG_BLOCKS))
+    src = VGResNet101Backbone(weights=None)
+    src.load_state_dict(seeded, strict=True)
+    ck = {("RCNN_top.0." + k[9:] if k.startswith("RCNN_top.") else k): v for k, v in src.state_dict().items()}
+    ck["RCNN_rpn.RPN_Conv.weight"] = torch.zeros(4)
+    ck["RCNN_cls_score.weight"] = torch.zeros(4)
+    ck["RCNN_base.0.weight"] = torch.zeros(64, 3, 3, 3)
+    ck["RCNN_base.9.weight"] = torch.zeros(1)
+    path = str(tmp_path / "vg.pth")
+    torch.save({"model": ck}, path)
+    torch.manual_seed(3)
+    fresh = VGResNet101Backbone(weights=None)
+    stem = fresh.state_dict()["RCNN_base.0.weight"].clone()
+    stats = load_vg_backbone_weights(fresh, path)
+    assert [stats["loaded"], stats["total_model"], stats["skipped"]] == G["vg_loader_stats"].tolist()
+    assert stats["skipped_keys"] == [str(k) for k in G["vg_loader_skipped_keys"]]
+    got = fresh.state_dict()
+    assert torch.equal(got["RCNN_base.0.weight"], stem)                         # wrong shape in the checkpoint: kept
+    assert all(torch.equal(got[k], seeded[k]) for k in seeded if k != "RCNN_base.0.weight")
+
+
+@pytest.mark.gpu
+def test_vg_grid_features_vs_reference():
+    from PIL import Image
+    from multimodal_classification_b200.resnet_grid import ResNetVGExtractor
+    ext = ResNetVGExtractor(device="cuda", weights=None, weights_path="/nonexistent.pth")
+    assert not ext.has_vg_weights and ext.grid_size == 6
+    ext.backbone.load_state_dict(ro.vg_backbone_state(ro.seeded_backbone_state(1, VG_BLOCKS)), strict=True)
+    feats, spatial = ext.extract_features(Image.fromarray(G["image_u8"]))
+    assert feats.shape == (36, 2048) and np.array_equal(spatial.cpu().numpy(), G["vg_spatial_36"])
+    ref, got = G["vg_features_36"], feats.cpu().numpy()[:, ::4]
+    rel, mx = np.linalg.norm(got - ref) / np.linalg.norm(ref), np.abs(got - ref).max() / np.abs(ref).max()
+    print(f"vg grid features: rel-L2 {rel:.4f}  max-rel {mx:.4f}")
+    assert rel <= 2e-2 and mx <= 2e-2, (rel, mx)
