@@ -197,6 +197,25 @@ def epoch_order(n: int, shuffle: bool) -> List[int]:
     return torch.randperm(n, generator=g).tolist()
 
 
+def shard_order(n: int, shuffle: bool, rank: int, world_size: int, seed: int = 0, epoch: int = 0) -> List[int]:
+    """This rank's sample order for data-parallel training (disjoint shards, one process per GPU): the index
+    arithmetic of ``torch.utils.data.distributed.DistributedSampler(drop_last=False)`` — a permutation seeded by
+    ``seed + epoch`` shared by all ranks, padded by wrapping to a multiple of ``world_size``, then every ``world_size``-th
+    index starting at ``rank``.  Every rank gets the same number of samples, so the ranks' collectives stay in step."""
+    if shuffle:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        order = torch.randperm(n, generator=g).tolist()
+    else:
+        order = list(range(n))
+    if n == 0:
+        return []
+    total = (n + world_size - 1) // world_size * world_size
+    pad = total - n
+    order += (order * ((pad + n - 1) // n))[:pad]
+    return order[rank:total:world_size]
+
+
 def batch_plan(order: Sequence[int], batch_size: int, drop_last: bool) -> List[List[int]]:
     out = [list(order[i:i + batch_size]) for i in range(0, len(order), batch_size)]
     if drop_last and out and len(out[-1]) < batch_size:
@@ -235,12 +254,14 @@ class _Slot:
 class FeatureStoreLoader:
     """Iterable of reference-shaped batch dicts resident on ``device`` (see the module docstring).
 
+    ``rank`` / ``world_size`` > 1 shard every epoch like ``DistributedSampler`` (one loader per process / GPU, call
+    ``set_epoch`` each epoch); with one process the order is the reference ``DataLoader``'s.
     ``feature_dtype=torch.bfloat16`` (default) hands the encoder its GEMM operand directly; ``torch.float32`` yields batches
     bit-identical to the reference loader's (the encoder then rounds them itself — same result)."""
 
     def __init__(self, data, records, tokenizer, max_seq_length: int = 128, batch_size: int = 32, shuffle: bool = False,
                  drop_last: bool = False, device="cuda", depth: int = 3, feature_dtype: torch.dtype = torch.bfloat16,
-                 start_delay_ms: float = 1.0):
+                 start_delay_ms: float = 1.0, rank: int = 0, world_size: int = 1, seed: int = 0):
         if not torch.cuda.is_available():
             raise VbError("FeatureStoreLoader stages batches in HBM and needs a CUDA device; there is no CPU fall-back")
         if depth < 2:
@@ -249,6 +270,9 @@ class FeatureStoreLoader:
             raise VbError("feature_dtype must be bfloat16 or float32")
         self.dataset = TextTable(data, tokenizer, max_seq_length)
         self.records, self.batch_size, self.shuffle, self.drop_last = records, batch_size, shuffle, drop_last
+        if not 0 <= rank < world_size:
+            raise VbError(f"rank {rank} outside world of {world_size}")
+        self.rank, self.world_size, self.seed, self.epoch = rank, world_size, seed, 0
         self.device = torch.device(device if str(device) != "cuda" else f"cuda:{torch.cuda.current_device()}")
         self.depth, self.feature_dtype, self.start_delay = depth, feature_dtype, start_delay_ms * 1e-3
         self._layouts: Dict[int, BatchLayout] = {}
@@ -258,8 +282,17 @@ class FeatureStoreLoader:
             self._slots = [_Slot(full, self.device, feature_dtype) for _ in range(depth)]
         self.h2d_bytes = 0            # bytes shipped host -> device so far (for the bench's e2e accounting)
 
+    def set_epoch(self, epoch: int) -> None:
+        """Data-parallel shuffling is seeded by ``seed + epoch`` (as ``DistributedSampler.set_epoch``)."""
+        self.epoch = epoch
+
+    def _order(self) -> List[int]:
+        if self.world_size == 1:
+            return epoch_order(len(self.dataset), self.shuffle)        # the reference loader's order (global torch RNG)
+        return shard_order(len(self.dataset), self.shuffle, self.rank, self.world_size, self.seed, self.epoch)
+
     def __len__(self) -> int:
-        n = len(self.dataset)
+        n = (len(self.dataset) + self.world_size - 1) // self.world_size
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def _layout(self, b: int) -> BatchLayout:
@@ -305,7 +338,7 @@ class FeatureStoreLoader:
 
     # consumer side -------------------------------------------------------------------------------------------------
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
-        plan = batch_plan(epoch_order(len(self.dataset), self.shuffle), self.batch_size, self.drop_last)
+        plan = batch_plan(self._order(), self.batch_size, self.drop_last)
         out: "queue.Queue" = queue.Queue()
         free: "queue.Queue" = queue.Queue()
         for i in range(self.depth):
@@ -348,9 +381,14 @@ def _bert_tokenizer():
 
 
 def _three(train_data, val_data, test_data, records, tokenizer, batch_size, max_seq_length, device, depth):
+    """Train: shuffled, drop_last, sharded over the ranks of an initialised process group (one process per GPU);
+    validation / test: sequential and whole on every rank, as the reference evaluates them."""
+    import torch.distributed as dist
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
     def make(data, train):
         return FeatureStoreLoader(data, records, tokenizer, max_seq_length, batch_size, shuffle=train, drop_last=train,
-                                  device=device, depth=depth)
+                                  device=device, depth=depth, rank=rank if train else 0, world_size=world if train else 1)
     return make(train_data, True), make(val_data, False), make(test_data, False)
 
 

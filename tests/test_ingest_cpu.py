@@ -100,3 +100,23 @@ def test_ragged_record_is_an_error_and_loader_needs_cuda():
     if not torch.cuda.is_available():
         with pytest.raises(VbError, match="no CPU fall-back"):
             ingest.FeatureStoreLoader(frame(), rec, tokenizer(), T)
+
+
+def test_shard_order_is_distributed_samplers():
+    """Per-rank order = torch's DistributedSampler (same seed / epoch), for even and ragged splits, shuffled or not; the
+    ranks' shards have equal length and together cover every sample."""
+    from torch.utils.data.distributed import DistributedSampler
+    from multimodal_classification_b200 import ingest
+    for n, world in [(37, 2), (40, 4), (5, 8), (1, 2), (64, 8)]:
+        data = list(range(n))
+        for shuffle in (False, True):
+            for epoch in (0, 3):
+                shards = []
+                for rank in range(world):
+                    ref = DistributedSampler(data, num_replicas=world, rank=rank, shuffle=shuffle, seed=11)
+                    ref.set_epoch(epoch)
+                    got = ingest.shard_order(n, shuffle, rank, world, seed=11, epoch=epoch)
+                    assert got == list(ref), (n, world, rank, shuffle, epoch)
+                    shards.append(got)
+                assert len({len(s) for s in shards}) == 1 and set().union(*shards) == set(data)
+    assert ingest.shard_order(0, True, 1, 2) == []

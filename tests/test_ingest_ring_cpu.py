@@ -95,3 +95,27 @@ def test_ring_errors_early_exit_and_empty_split(ingest_on_cpu):
     assert len(empty) == 0 and list(empty) == []
     with pytest.raises(ingest.VbError):
         ingest.FeatureStoreLoader(frame(), ingest.LMDBRecords(store().get, R, F), tokenizer(), T, 2, device="cpu", depth=1)
+
+
+def test_two_ranks_get_disjoint_equal_shards(ingest_on_cpu):
+    """Two loaders as two data-parallel ranks would build them: same epoch permutation, disjoint halves, equal batch counts;
+    set_epoch changes the permutation for both alike."""
+    ingest = ingest_on_cpu
+    rec = ingest.LMDBRecords(store().get, R, F)
+    loaders = [ingest.FeatureStoreLoader(frame(), rec, tokenizer(), T, 2, shuffle=True, drop_last=False, device="cpu", rank=r,
+                                         world_size=2, seed=5) for r in range(2)]
+    assert len(loaders[0]) == len(loaders[1]) == 3          # 11 samples -> 6 per rank (one wrapped) -> 3 batches of 2
+    seen = []
+    for epoch in (0, 1):
+        per_rank = []
+        for ld in loaders:
+            ld.set_epoch(epoch)
+            per_rank.append(np.concatenate([b["input_ids"].numpy() for b in ld]))
+        assert per_rank[0].shape == per_rank[1].shape == (6, T)
+        seen.append(np.concatenate(per_rank))
+    all_ids = np.concatenate([b["input_ids"] for b in golden_batches("lmdb_seq")])
+    for rows in seen:                                        # 12 rows = the 11 distinct samples + one wrapped duplicate
+        assert {r.tobytes() for r in rows} == {r.tobytes() for r in all_ids}
+    assert not np.array_equal(seen[0], seen[1])
+    with pytest.raises(ingest.VbError):
+        ingest.FeatureStoreLoader(frame(), rec, tokenizer(), T, 2, device="cpu", rank=2, world_size=2)
