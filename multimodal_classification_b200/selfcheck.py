@@ -79,6 +79,23 @@ def compare_roi_stage(verbose=True):
     return err
 
 
+def compare_ingest(verbose=True):
+    """One LMDB-shaped batch through vb_lmdb_regions against the oracle: spatial rows bit-exact, features = RNE bf16."""
+    from oracle import ingest_oracle as io
+    from . import ops
+    import numpy as np
+    rng = np.random.default_rng(3)
+    feat = np.abs(rng.standard_normal((4 * 100, 2048))).astype(np.float32)
+    boxes = rng.uniform(0, 1000, (4 * 100, 4)).astype(np.float32)
+    f16 = torch.empty(400, 2048, dtype=torch.bfloat16, device="cuda")
+    spatial = torch.empty(400, 5, device="cuda")
+    ops.lmdb_regions(torch.from_numpy(feat).cuda(), f16, torch.from_numpy(boxes).cuda(), spatial)
+    assert np.array_equal(spatial.cpu().numpy(), io.process_boxes(boxes, 400))
+    assert torch.equal(f16.cpu().view(torch.int16), torch.from_numpy(feat).to(torch.bfloat16).view(torch.int16))
+    if verbose:
+        print("[selfcheck] ingest: spatial rows and bf16 features bit-exact")
+
+
 def smoke():
     if not torch.cuda.is_available():
         raise RuntimeError("smoke() needs a CUDA device")
@@ -88,4 +105,5 @@ def smoke():
     torch.cuda.set_device(0)
     compare_with_oracle(vo.tiny_config(), dict(batch=4, seq=128, regions=100, seed=1234))
     compare_roi_stage()
+    compare_ingest()
     print("[selfcheck] smoke OK")
