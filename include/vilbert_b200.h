@@ -187,7 +187,7 @@ int vb_cls_ce_bwd(const void* h, const float* w, const int32_t* labels, const fl
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Fused softmax attention on tcgen05/TMEM: one CTA per (sample, head), sq, sk <= 128, d in {64,128}.
+ * Fused softmax attention on tcgen05/TMEM: one CTA per (sample, head), sq, sk <= 128 per call, d in {64,128}.
  *   out = dropout(softmax(q k^T * scale + mask_bias[b, key])) v
  * Serves BertSelfAttention (models/vilbert_facebook_arch.py:126-144) and both directions of BiAttention (:253-294):
  * q, k, v are independent strided views (pointer to the first head's column, row stride in elements, sq / sk rows
@@ -205,9 +205,30 @@ typedef struct vb_attn_args {
   const void* dout; int64_t lddo;                /* backward */
   void* dq; void* dk; void* dv;
   int64_t lddq, lddk, lddv;
+  /* Block views, for sequences above 128 (0 = the block is the whole sequence): q / out / dout / dq address sample b at row
+   * b * q_batch_rows, k / v / dk / dv at row b * k_batch_rows, mask_bias at b * bias_ld; rows past sq / sk are not touched. */
+  int64_t q_batch_rows, k_batch_rows, bias_ld;
+  const float* delta;                            /* backward of a key block: sum over ALL keys of P dP per row, fp32
+                                                    [batch, heads, 128] (vb_attn_delta); NULL = this block holds all keys */
 } vb_attn_args;
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
 int vb_attention_bwd(const vb_attn_args* args, void* stream);
+
+/* Longer sequences (e.g. 257 DINOv2 patch tokens as regions, BASELINE config 4) run as blocks of <= 128 queries x <= 128 keys
+ * through the two entry points above; these three kernels join the blocks (flash-attention algebra, host loop in ops.py):
+ *   vb_attn_merge : out = sum_j exp(lse_j - LSE) o_j, LSE = log sum_j exp(lse_j) over n_parts <= 4 key blocks; o_parts /
+ *                   lse_parts are HOST arrays of device pointers (bf16 [.., heads*d] views with row stride ldp, fp32
+ *                   [batch, heads, 128]); writes out (bf16, row stride ldo) and lse_out.
+ *   vb_attn_delta : delta[b, h, row] = sum_d dout * out over one head's columns (= sum_k P dP over all keys).
+ *   vb_sum_rows_bf16 : dst[r, c] = sum_p parts[p][r, c] (fp32 accumulation) for the dq / dk / dv partials of the blocks.
+ * Row r of sample b lives at row b * batch_rows + r of every view; sq rows per sample are processed. */
+int vb_attn_merge(const void* const* o_parts, const float* const* lse_parts, int32_t n_parts, int64_t ldp, void* out,
+                  int64_t ldo, float* lse_out, int32_t batch, int32_t heads, int32_t sq, int64_t batch_rows, int32_t d,
+                  void* stream);
+int vb_attn_delta(const void* out, int64_t ldo, const void* dout, int64_t lddo, float* delta, int32_t batch, int32_t heads,
+                  int32_t sq, int64_t batch_rows, int32_t d, void* stream);
+int vb_sum_rows_bf16(const void* const* parts, int32_t n_parts, int64_t ldp, void* dst, int64_t ldd, int64_t rows,
+                     int32_t width, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * ResNet-152 RoI feature stage (models/feature_extractors/resnet152_roi.py).  Activations are NHWC bf16; every

@@ -65,6 +65,7 @@ class AttnArgs(C.Structure):
         ("scale", C.c_float), ("p_drop", C.c_float), ("site", C.c_uint32), ("seed", C.c_void_p),
         ("dout", C.c_void_p), ("lddo", C.c_int64), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
         ("lddq", C.c_int64), ("lddk", C.c_int64), ("lddv", C.c_int64),
+        ("q_batch_rows", C.c_int64), ("k_batch_rows", C.c_int64), ("bias_ld", C.c_int64), ("delta", C.c_void_p),
     ]
 
 
@@ -133,6 +134,9 @@ def _declare(l: C.CDLL) -> None:
         "vb_box_area_score": [vp, i32, f32, f32, f32, vp, vp],
         "vb_nms": [vp, vp, i32, f32, vp, vp, vp, vp],
         "vb_lmdb_regions": [vp, vp, i64, vp, vp, i32, i32, f32, f32, vp],
+        "vb_attn_merge": [vp, vp, i32, i64, vp, i64, vp, i32, i32, i32, i64, i32, vp],
+        "vb_attn_delta": [vp, i64, vp, i64, vp, i32, i32, i32, i64, i32, vp],
+        "vb_sum_rows_bf16": [vp, i32, i64, vp, i64, i64, i32, vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(l, name)

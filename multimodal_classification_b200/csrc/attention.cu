@@ -24,6 +24,8 @@ struct AttnKernelParams {
   __nv_bfloat16* out;
   __nv_bfloat16 *dq, *dk, *dv;
   long long ldo, lddq, lddk, lddv;
+  long long q_rows, k_rows, bias_ld;   // rows between consecutive samples in the q- / k-side views; mask row stride
+  const float* delta;                   // backward: external sum_k P dP per row ([batch, heads, 128]) or null
   int sq, sk, heads;
   float scale, p_drop;
   uint32_t site;
@@ -116,7 +118,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  if (tid < 128) sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.sk + tid] : 0.f) : -INFINITY;
+  if (tid < 128) sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.bias_ld + tid] : 0.f) : -INFINITY;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -191,7 +193,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   mbar_wait(&bars[1], 1);
   __syncwarp();
   tc_fence_after();
-  store_tmem_cols<D / 64>(trow + 128 + ch * (D / 2), p.out + ((long long)b * p.sq + row) * p.ldo + h * D + ch * (D / 2), row < p.sq);
+  store_tmem_cols<D / 64>(trow + 128 + ch * (D / 2), p.out + ((long long)b * p.q_rows + row) * p.ldo + h * D + ch * (D / 2), row < p.sq);
 
   tc_fence_before();
   __syncthreads();
@@ -229,7 +231,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  if (tid < 128) sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.sk + tid] : 0.f) : -INFINITY;
+  if (tid < 128) sBias[tid] = tid < p.sk ? (p.mask_bias ? p.mask_bias[(long long)b * p.bias_ld + tid] : 0.f) : -INFINITY;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -293,7 +295,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
   sRed[tid] = make_float2(part, 0.f);
   __syncthreads();
-  const float drow = part + sRed[tid ^ 128].x;
+  // key-blocked calls (sequences above 128) pass the row's sum over ALL key blocks; a single block computes it here
+  const float drow = p.delta ? p.delta[((long long)b * p.heads + h) * 128 + row] : part + sRed[tid ^ 128].x;
 #pragma unroll
   for (int i = 0; i < 64; ++i) pr[i] = pr[i] * (dp[i] - drow) * p.scale;   // dS (scaled so that dQ = dS K, dK = dS^T Q)
   store_half_row_bf16(sdS + ch * ATT_CHUNK, row, pr);
@@ -321,9 +324,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncwarp();
   tc_fence_after();
   constexpr int HD = D / 2;   // each of the two threads of a row stores half of the head width
-  store_tmem_cols<D / 64>(trow + ch * HD, p.dq + ((long long)b * p.sq + row) * p.lddq + h * D + ch * HD, row < p.sq);
-  store_tmem_cols<D / 64>(trow + 256 + ch * HD, p.dv + ((long long)b * p.sk + row) * p.lddv + h * D + ch * HD, row < p.sk);
-  store_tmem_cols<D / 64>(trow + 384 + ch * HD, p.dk + ((long long)b * p.sk + row) * p.lddk + h * D + ch * HD, row < p.sk);
+  store_tmem_cols<D / 64>(trow + ch * HD, p.dq + ((long long)b * p.q_rows + row) * p.lddq + h * D + ch * HD, row < p.sq);
+  store_tmem_cols<D / 64>(trow + 256 + ch * HD, p.dv + ((long long)b * p.k_rows + row) * p.lddv + h * D + ch * HD, row < p.sk);
+  store_tmem_cols<D / 64>(trow + 384 + ch * HD, p.dk + ((long long)b * p.k_rows + row) * p.lddk + h * D + ch * HD, row < p.sk);
 
   tc_fence_before();
   __syncthreads();
@@ -335,9 +338,10 @@ static constexpr int attn_smem_bytes(bool bwd) {
   return (bwd ? 4 : 3) * (D / 64) * ATT_CHUNK + (bwd ? 4 : 2) * ATT_CHUNK + 128 * 4 + ATT_THREADS * 8 + 64 + 1024;
 }
 
-static int make_view_map(CUtensorMap* m, const void* base, int width, int seq, int batch, long long ld) {
-  // [batch, seq, width] view with row stride ld; box = 64 columns x 128 rows x 1 sample
-  return make_tensor_map_3d(m, base, width, seq, batch, ld, (long long)seq * ld, 64, 128, 1);
+static int make_view_map(CUtensorMap* m, const void* base, int width, int seq, int batch, long long ld, long long batch_rows) {
+  // [batch, seq, width] view with row stride ld and batch_rows rows between samples (> seq when the view is one block of a
+  // longer sequence: rows past `seq` are zero-filled by TMA either way); box = 64 columns x 128 rows x 1 sample
+  return make_tensor_map_3d(m, base, width, seq, batch, ld, batch_rows * ld, 64, 128, 1);
 }
 
 template <int D>
@@ -345,13 +349,15 @@ static int launch_attn(const vb_attn_args& a, bool bwd, cudaStream_t stream) {
   CUtensorMap mq, mk, mv, mdo;
   const int width = a.heads * D;
   int rc;
-  if ((rc = make_view_map(&mq, a.q, width, a.sq, a.batch, a.ldq)) != VB_OK) return rc;
-  if ((rc = make_view_map(&mk, a.k, width, a.sk, a.batch, a.ldk)) != VB_OK) return rc;
-  if ((rc = make_view_map(&mv, a.v, width, a.sk, a.batch, a.ldv)) != VB_OK) return rc;
+  const long long q_rows = a.q_batch_rows > 0 ? a.q_batch_rows : a.sq, k_rows = a.k_batch_rows > 0 ? a.k_batch_rows : a.sk;
+  if ((rc = make_view_map(&mq, a.q, width, a.sq, a.batch, a.ldq, q_rows)) != VB_OK) return rc;
+  if ((rc = make_view_map(&mk, a.k, width, a.sk, a.batch, a.ldk, k_rows)) != VB_OK) return rc;
+  if ((rc = make_view_map(&mv, a.v, width, a.sk, a.batch, a.ldv, k_rows)) != VB_OK) return rc;
   AttnKernelParams p;
   p.lse = a.lse; p.mask_bias = a.mask_bias; p.out = (__nv_bfloat16*)a.out;
   p.dq = (__nv_bfloat16*)a.dq; p.dk = (__nv_bfloat16*)a.dk; p.dv = (__nv_bfloat16*)a.dv;
   p.ldo = a.ldo; p.lddq = a.lddq; p.lddk = a.lddk; p.lddv = a.lddv;
+  p.q_rows = q_rows; p.k_rows = k_rows; p.bias_ld = a.bias_ld > 0 ? a.bias_ld : a.sk; p.delta = a.delta;
   p.sq = a.sq; p.sk = a.sk; p.heads = a.heads; p.scale = a.scale; p.p_drop = a.p_drop; p.site = a.site;
   p.seed = (const unsigned long long*)a.seed;
   dim3 grid(a.heads, a.batch);
@@ -363,7 +369,7 @@ static int launch_attn(const vb_attn_args& a, bool bwd, cudaStream_t stream) {
     }
     attn_fwd_kernel<D><<<grid, ATT_THREADS, attn_smem_bytes<D>(false), stream>>>(mq, mk, mv, p);
   } else {
-    if ((rc = make_view_map(&mdo, a.dout, width, a.sq, a.batch, a.lddo)) != VB_OK) return rc;
+    if ((rc = make_view_map(&mdo, a.dout, width, a.sq, a.batch, a.lddo, q_rows)) != VB_OK) return rc;
     static bool attr = false;
     if (!attr) {
       VB_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<D>(true)));
@@ -381,6 +387,8 @@ static int check_attn(const vb_attn_args* a, bool bwd) {
   VB_REQUIRE(a->d == 64 || a->d == 128, "head width must be 64 or 128");
   VB_REQUIRE(a->sq >= 1 && a->sq <= 128 && a->sk >= 1 && a->sk <= 128, "1 <= sq, sk <= 128");
   VB_REQUIRE(a->batch >= 1 && a->heads >= 1, "batch and heads must be positive");
+  VB_REQUIRE((a->q_batch_rows == 0 || a->q_batch_rows >= a->sq) && (a->k_batch_rows == 0 || a->k_batch_rows >= a->sk) &&
+             (a->bias_ld == 0 || a->bias_ld >= a->sk), "per-sample row counts must cover the block");
   VB_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0, "leading dimensions must be multiples of 8");
   VB_REQUIRE(((uintptr_t)a->q & 15) == 0 && ((uintptr_t)a->k & 15) == 0 && ((uintptr_t)a->v & 15) == 0, "q/k/v must be 16-byte aligned");
   VB_REQUIRE(a->p_drop >= 0.f && a->p_drop < 1.f && (a->p_drop == 0.f || a->seed), "dropout p in [0,1) with a device seed");

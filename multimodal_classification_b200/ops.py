@@ -285,13 +285,38 @@ def cls_ce_bwd(h, w, labels, probs, dloss, dlogits_ext, dw, db, dh):
 
 
 # ------------------------------------------------------------------------------------------------ attention
+ATTN_BLOCK = 128            # queries / keys one fused-attention CTA handles
+ATTN_MAX_SEQ = 4 * ATTN_BLOCK   # vb_attn_merge / vb_sum_rows_bf16 join at most four blocks
+_BLOCK_SITE_STRIDE = 1 << 16  # dropout sites of the blocks of one attention call (engine sites are far below this)
+_attn_scratch = {}            # (kind, output data_ptr, geometry) -> buffers that outlive the call (CUDA-graph replays)
+
+
+def attn_blocks(s: int):
+    """[(start, length)] of the balanced blocks of <= 128 a sequence of s positions is processed in."""
+    n = (s + ATTN_BLOCK - 1) // ATTN_BLOCK
+    base, rem = divmod(s, n)
+    out, start = [], 0
+    for i in range(n):
+        ln = base + (1 if i < rem else 0)
+        out.append((start, ln))
+        start += ln
+    return out
+
+
+def attn_lse_numel(batch: int, heads: int, sq: int) -> int:
+    """Elements of the fp32 log-sum-exp buffer forward writes and backward reads: [query blocks, batch, heads, 128]."""
+    return len(attn_blocks(sq)) * batch * heads * 128
+
+
 def _attn_args(q, k, v, lse, mask_bias_t, batch, heads, sq, sk, d, scale, p_drop, site, seed):
     _need_cuda(q, k, v, lse, mask_bias_t, seed)
     for t in (q, k, v):
         assert t.dtype == torch.bfloat16 and t.stride(-1) == 1 and t.dim() == 2
     assert q.shape[0] == batch * sq and k.shape[0] == batch * sk and v.shape[0] == batch * sk
     assert q.shape[1] == heads * d and k.shape[1] == heads * d and v.shape[1] == heads * d
-    assert lse.dtype == torch.float32 and lse.numel() == batch * heads * 128
+    assert lse.dtype == torch.float32 and lse.numel() == attn_lse_numel(batch, heads, sq)
+    if sq > ATTN_MAX_SEQ or sk > ATTN_MAX_SEQ:
+        raise _lib.VbError(f"attention over more than {ATTN_MAX_SEQ} positions is not supported (sq={sq}, sk={sk})")
     a = _lib.AttnArgs()
     a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     a.ldq, a.ldk, a.ldv = q.stride(0), k.stride(0), v.stride(0)
@@ -303,30 +328,127 @@ def _attn_args(q, k, v, lse, mask_bias_t, batch, heads, sq, sk, d, scale, p_drop
     return a
 
 
+def _block_view(a, full, i, j, q0, ql, k0, kl, sq, sk, nkb):
+    """Copy of the whole-sequence argument block `full`, narrowed to query block i (rows q0 .. q0+ql) x key block j."""
+    C.memmove(C.byref(a), C.byref(full), C.sizeof(_lib.AttnArgs))
+    a.q = full.q + q0 * full.ldq * 2
+    a.k = full.k + k0 * full.ldk * 2
+    a.v = full.v + k0 * full.ldv * 2
+    a.sq, a.sk, a.q_batch_rows, a.k_batch_rows, a.bias_ld = ql, kl, sq, sk, sk
+    if full.mask_bias:
+        a.mask_bias = full.mask_bias + k0 * 4
+    a.site = full.site + (i * nkb + j + 1) * _BLOCK_SITE_STRIDE          # an independent dropout stream per block
+    return a
+
+
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*ptrs)
+
+
+def _scratch(kind, anchor, shapes):
+    """Persistent scratch of one attention call site (keyed by its output tensor): allocated on the eager warm-up step,
+    found again on every later call, so that captured graphs keep valid addresses."""
+    key = (kind, anchor.data_ptr(), tuple(shapes))
+    got = _attn_scratch.get(key)
+    if got is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.VbError("attention scratch requested for the first time during graph capture (warm-up step missing)")
+        got = _attn_scratch[key] = [torch.empty(shape, dtype=dt, device=anchor.device) for shape, dt in shapes]
+    return got
+
+
 def attention_fwd(q, k, v, out, lse, *, batch, heads, sq, sk, d, mask_bias=None, scale=None, p_drop=0.0, site=0,
                   seed=None):
     """out = dropout(softmax(q k^T * scale + mask_bias)) v per (sample, head); q/k/v/out are 2-D strided views
-    [batch*seq, heads*d] (reference models/vilbert_facebook_arch.py:126-144 and :253-294)."""
+    [batch*seq, heads*d] (reference models/vilbert_facebook_arch.py:126-144 and :253-294).  Sequences above 128 run as
+    balanced blocks of <= 128 queries x <= 128 keys joined by vb_attn_merge; lse is [query blocks, batch, heads, 128]."""
     scale = (1.0 / d ** 0.5) if scale is None else scale
     a = _attn_args(q, k, v, lse, mask_bias, batch, heads, sq, sk, d, scale, p_drop, site, seed)
     _need_cuda(out)
-    assert out.shape == q.shape and out.stride(1) == 1
+    assert out.shape == q.shape and out.stride(1) == 1 and out.dtype == torch.bfloat16
     a.out, a.ldo = out.data_ptr(), out.stride(0)
-    _lib.check(_lib.lib().vb_attention_fwd(C.byref(a), _stream()), "vb_attention_fwd")
+    if sq <= ATTN_BLOCK and sk <= ATTN_BLOCK:
+        _lib.check(_lib.lib().vb_attention_fwd(C.byref(a), _stream()), "vb_attention_fwd")
+        return out
+    qb, kb = attn_blocks(sq), attn_blocks(sk)
+    nkb, width, blk = len(kb), heads * d, batch * heads * 128
+    parts = lses = None
+    if nkb > 1:      # per key block: a full-size partial output and its log-sum-exp for every query block
+        parts, lses = _scratch("fwd", out, [((nkb, batch * sq, width), torch.bfloat16), ((nkb, len(qb), blk), torch.float32)])
+    b = _lib.AttnArgs()
+    for i, (q0, ql) in enumerate(qb):
+        for j, (k0, kl) in enumerate(kb):
+            _block_view(b, a, i, j, q0, ql, k0, kl, sq, sk, nkb)
+            if nkb > 1:
+                b.out, b.ldo = parts[j].data_ptr() + q0 * width * 2, width
+                b.lse = lses[j, i].data_ptr()
+            else:
+                b.out = a.out + q0 * a.ldo * 2
+                b.lse = a.lse + i * blk * 4
+            _lib.check(_lib.lib().vb_attention_fwd(C.byref(b), _stream()), "vb_attention_fwd")
+        if nkb > 1:
+            _lib.check(_lib.lib().vb_attn_merge(_ptr_array([parts[j].data_ptr() + q0 * width * 2 for j in range(nkb)]),
+                                                _ptr_array([lses[j, i].data_ptr() for j in range(nkb)]), nkb, width,
+                                                a.out + q0 * a.ldo * 2, a.ldo, a.lse + i * blk * 4, batch, heads, ql, sq, d,
+                                                _stream()), "vb_attn_merge")
     return out
 
 
 def attention_bwd(dout, q, k, v, lse, dq, dk, dv, *, batch, heads, sq, sk, d, mask_bias=None, scale=None, p_drop=0.0,
-                  site=0, seed=None):
+                  site=0, seed=None, out=None):
+    """Backward of attention_fwd.  ``out`` (the forward output) is needed when the keys span more than one block."""
     scale = (1.0 / d ** 0.5) if scale is None else scale
     a = _attn_args(q, k, v, lse, mask_bias, batch, heads, sq, sk, d, scale, p_drop, site, seed)
-    _need_cuda(dout, dq, dk, dv)
+    _need_cuda(dout, dq, dk, dv, out)
     for t in (dout, dq, dk, dv):
         assert t.dtype == torch.bfloat16 and t.stride(1) == 1
     a.dout, a.lddo = dout.data_ptr(), dout.stride(0)
     a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     a.lddq, a.lddk, a.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
-    _lib.check(_lib.lib().vb_attention_bwd(C.byref(a), _stream()), "vb_attention_bwd")
+    if sq <= ATTN_BLOCK and sk <= ATTN_BLOCK:
+        _lib.check(_lib.lib().vb_attention_bwd(C.byref(a), _stream()), "vb_attention_bwd")
+        return
+    qb, kb = attn_blocks(sq), attn_blocks(sk)
+    nqb, nkb, width, blk = len(qb), len(kb), heads * d, batch * heads * 128
+    shapes = []
+    if nkb > 1:
+        if out is None:
+            raise _lib.VbError("attention_bwd over more than 128 keys needs the forward output (out=...)")
+        assert out.dtype == torch.bfloat16 and out.stride(1) == 1 and out.shape == q.shape
+        shapes += [((nkb, batch * sq, width), torch.bfloat16), ((nqb, blk), torch.float32)]      # dq partials, delta
+    if nqb > 1:
+        shapes += [((nqb, batch * sk, width), torch.bfloat16), ((nqb, batch * sk, width), torch.bfloat16)]   # dk, dv partials
+    bufs = _scratch("bwd", dq, shapes)
+    dq_parts, delta = (bufs[0], bufs[1]) if nkb > 1 else (None, None)
+    dk_parts, dv_parts = (bufs[-2], bufs[-1]) if nqb > 1 else (None, None)
+    b = _lib.AttnArgs()
+    for i, (q0, ql) in enumerate(qb):
+        if nkb > 1:
+            _lib.check(_lib.lib().vb_attn_delta(out.data_ptr() + q0 * out.stride(0) * 2, out.stride(0),
+                                                a.dout + q0 * a.lddo * 2, a.lddo, delta[i].data_ptr(), batch, heads, ql, sq, d,
+                                                _stream()), "vb_attn_delta")
+        for j, (k0, kl) in enumerate(kb):
+            _block_view(b, a, i, j, q0, ql, k0, kl, sq, sk, nkb)
+            b.lse = a.lse + i * blk * 4
+            b.dout = a.dout + q0 * a.lddo * 2
+            if nkb > 1:
+                b.delta = delta[i].data_ptr()
+                b.dq, b.lddq = dq_parts[j].data_ptr() + q0 * width * 2, width
+            else:
+                b.dq = a.dq + q0 * a.lddq * 2
+            if nqb > 1:
+                b.dk, b.lddk = dk_parts[i].data_ptr() + k0 * width * 2, width
+                b.dv, b.lddv = dv_parts[i].data_ptr() + k0 * width * 2, width
+            else:
+                b.dk, b.dv = a.dk + k0 * a.lddk * 2, a.dv + k0 * a.lddv * 2
+            _lib.check(_lib.lib().vb_attention_bwd(C.byref(b), _stream()), "vb_attention_bwd")
+    if nkb > 1:
+        _lib.check(_lib.lib().vb_sum_rows_bf16(_ptr_array([dq_parts[j].data_ptr() for j in range(nkb)]), nkb, width, a.dq,
+                                               a.lddq, batch * sq, width, _stream()), "vb_sum_rows_bf16")
+    if nqb > 1:
+        for parts, dst, ld in ((dk_parts, a.dk, a.lddk), (dv_parts, a.dv, a.lddv)):
+            _lib.check(_lib.lib().vb_sum_rows_bf16(_ptr_array([parts[i].data_ptr() for i in range(nqb)]), nqb, width, dst, ld,
+                                                   batch * sk, width, _stream()), "vb_sum_rows_bf16")
 
 
 # ------------------------------------------------------------------------------------------------ RoI feature stage

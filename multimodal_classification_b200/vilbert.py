@@ -479,7 +479,7 @@ class _Engine:
         qkv = pl.buf(tag + ".qkv", (M, 3 * H))
         self._linear(x, p + ".attention.self.query.weight", qkv, rows=3 * H)
         ctx = pl.buf(tag + ".ctx", (M, H))
-        lse = pl.buf(tag + ".lse", (pl.B, heads, 128), torch.float32)
+        lse = pl.buf(tag + ".lse", (len(ops.attn_blocks(S)) * pl.B, heads, 128), torch.float32)
         sv["attn_site"] = self._next_site()
         ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, lse, batch=pl.B, heads=heads, sq=S, sk=S,
                           d=H // heads, mask_bias=bias, p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"],
@@ -523,7 +523,8 @@ class _Engine:
         qkv = sv["qkv"]
         ops.attention_bwd(g_ctx, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["lse"], g_qkv[:, :H], g_qkv[:, H:2 * H],
                           g_qkv[:, 2 * H:], batch=pl.B, heads=heads, sq=S, sk=S, d=H // heads, mask_bias=bias,
-                          p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"], seed=self.seed if pl.dropout else None)
+                          p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"], seed=self.seed if pl.dropout else None,
+                          out=sv["ctx"])
         self._linear_bwd(g_qkv, sv["x"], p + ".attention.self.query.weight", rows=3 * H, dx=dx_out,
                          aux=g_xres if g_xres is not None else g_ao, aux_mode=ops.AUX_ADD)
         self._scratch_end(pl, sc)
@@ -624,7 +625,7 @@ class _Engine:
         sv["site_v"], sv["site_t"] = self._next_site(), self._next_site()
         # text FFN half on the text stream
         t_ctx = pl.buf(tag + ".t_ctx", (Mt, bi))
-        t_lse = pl.buf(tag + ".t_lse", (B, heads, 128), torch.float32)
+        t_lse = pl.buf(tag + ".t_lse", (len(ops.attn_blocks(T)) * B, heads, 128), torch.float32)
         ops.attention_fwd(tqkv[:, :bi], vqkv[:, bi:2 * bi], vqkv[:, 2 * bi:], t_ctx, t_lse, batch=B, heads=heads, sq=T,
                           sk=R, d=d, mask_bias=pl.v_bias, p_drop=pa if drop else 0.0, site=sv["site_t"],
                           seed=self.seed if drop else None)
@@ -641,7 +642,7 @@ class _Engine:
         sv["t_ln2"] = self._ln(pl, t_fo, t_att, p + ".t_output.LayerNorm", t_out, tag + ".t_ln2", p_in=ph)
         with torch.cuda.stream(s_v):
             v_ctx = pl.buf(tag + ".v_ctx", (Mv, bi))
-            v_lse = pl.buf(tag + ".v_lse", (B, heads, 128), torch.float32)
+            v_lse = pl.buf(tag + ".v_lse", (len(ops.attn_blocks(R)) * B, heads, 128), torch.float32)
             ops.attention_fwd(vqkv[:, :bi], tqkv[:, bi:2 * bi], tqkv[:, 2 * bi:], v_ctx, v_lse, batch=B, heads=heads, sq=R,
                               sk=T, d=d, mask_bias=pl.t_bias, p_drop=pa if drop else 0.0, site=sv["site_v"],
                               seed=self.seed if drop else None)
@@ -804,11 +805,11 @@ class _Engine:
             # regions attend to tokens: dq -> visual q1, dk/dv -> text k2/v2
             ops.attention_bwd(g_vctx, vqkv[:, :bi], tqkv[:, bi:2 * bi], tqkv[:, 2 * bi:], sv["v_lse"], g_vqkv[:, :bi],
                               g_tqkv[:, bi:2 * bi], g_tqkv[:, 2 * bi:], batch=B, heads=heads, sq=R, sk=T, d=d,
-                              mask_bias=pl.t_bias, p_drop=pa if drop else 0.0, site=sv["site_v"], seed=seed)
+                              mask_bias=pl.t_bias, p_drop=pa if drop else 0.0, site=sv["site_v"], seed=seed, out=sv["v_ctx"])
         # tokens attend to regions: dq -> text q2, dk/dv -> visual k1/v1
         ops.attention_bwd(g_tctx, tqkv[:, :bi], vqkv[:, bi:2 * bi], vqkv[:, 2 * bi:], sv["t_lse"], g_tqkv[:, :bi],
                           g_vqkv[:, bi:2 * bi], g_vqkv[:, 2 * bi:], batch=B, heads=heads, sq=T, sk=R, d=d,
-                          mask_bias=pl.v_bias, p_drop=pa if drop else 0.0, site=sv["site_t"], seed=seed)
+                          mask_bias=pl.v_bias, p_drop=pa if drop else 0.0, site=sv["site_t"], seed=seed, out=sv["t_ctx"])
         s_t.wait_stream(s_v)
         s_v.wait_stream(s_t)
         self._linear_bwd(g_tqkv, sv["t_in"], p + ".biattention.query2.weight", rows=3 * bi, dx=dt_out,
@@ -982,8 +983,8 @@ class ViLBERTForClassification(nn.Module):
             eng = self._ensure_engine(device)
             B, T = input_ids.shape
             R = visual_features.shape[1]
-            if T > 128 or R > 128:
-                raise VbError(f"sequence lengths above 128 are not supported by the fused attention (T={T}, R={R})")
+            if T > ops.ATTN_MAX_SEQ or R > ops.ATTN_MAX_SEQ:
+                raise VbError(f"sequence lengths above {ops.ATTN_MAX_SEQ} are not supported by the blocked attention (T={T}, R={R})")
             if visual_features.shape[2] != cfg["v_feature_size"] or spatial_locations.shape[-1] != cfg["v_loc_size"]:
                 raise VbError("visual feature / location width does not match the configuration")
             need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())

@@ -39,6 +39,12 @@ CASES = [
     (2, 12, 40, 40, 64, True),
     (1, 1, 1, 1, 64, False),
     (2, 8, 128, 36, 128, False),
+    # above 128 positions: balanced blocks joined by vb_attn_merge / vb_attn_delta / vb_sum_rows_bf16 (BASELINE config 4)
+    (2, 8, 257, 257, 128, True),     # 257 DINOv2 tokens as regions: visual self-attention, 3 x 3 blocks
+    (2, 8, 128, 257, 128, True),     # tokens attend to 257 regions: key blocks only
+    (2, 8, 257, 128, 128, True),     # 257 regions attend to tokens: query blocks only
+    (1, 12, 300, 200, 64, False),    # ragged, 64-wide heads
+    (1, 2, 512, 129, 64, True),      # the maximum of four blocks
 ]
 
 
@@ -56,7 +62,7 @@ def test_attention_forward_backward(b, heads, sq, sk, d, masked):
         bias = torch.empty(b, sk, device="cuda")
         ops.mask_bias(mask, bias)
     out = torch.zeros(b * sq, H, dtype=torch.bfloat16, device="cuda")
-    lse = torch.empty(b, heads, 128, device="cuda")
+    lse = torch.empty(ops.attn_lse_numel(b, heads, sq), device="cuda")
     ops.attention_fwd(q, k, v, out, lse, batch=b, heads=heads, sq=sq, sk=sk, d=d, mask_bias=bias)
     qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
     ref = _ref(qr, kr, vr, bias, b, heads, sq, sk, d)
@@ -66,7 +72,7 @@ def test_attention_forward_backward(b, heads, sq, sk, d, masked):
     dqkv_q = torch.zeros(b * sq, 3 * H, dtype=torch.bfloat16, device="cuda")
     dqkv_k = torch.zeros(b * sk, 3 * H, dtype=torch.bfloat16, device="cuda")
     dq, dk, dv = dqkv_q[:, :H], dqkv_k[:, H:2 * H], dqkv_k[:, 2 * H:]
-    ops.attention_bwd(dout, q, k, v, lse, dq, dk, dv, batch=b, heads=heads, sq=sq, sk=sk, d=d, mask_bias=bias)
+    ops.attention_bwd(dout, q, k, v, lse, dq, dk, dv, batch=b, heads=heads, sq=sq, sk=sk, d=d, mask_bias=bias, out=out)
     _close(dq, qr.grad)
     _close(dk, kr.grad)
     _close(dv, vr.grad)
@@ -106,3 +112,36 @@ def test_attention_dropout_consistency():
     lhs = (o3.float() * dout.float()).sum().item()
     rhs = (dvk.float() * dirv.float()).sum().item()
     assert abs(lhs - rhs) <= 2e-2 * abs(lhs) + 1.0, (lhs, rhs)
+
+
+def test_blocked_attention_dropout_is_consistent_between_forward_and_backward():
+    """Sequences above 128 with dropout: the blocks' masks are regenerated by backward (directional finite difference of the
+    kernel's own forward, as above) and the kept fraction is 1 - p."""
+    from multimodal_classification_b200 import ops
+    b, heads, sq, sk, d, p = 2, 8, 257, 200, 128, 0.1
+    H = heads * d
+    q, k, v = _bf((b * sq, H), 11, 0.5), _bf((b * sk, H), 12, 0.5), _bf((b * sk, H), 13, 1.0)
+    seed = torch.tensor([1234], dtype=torch.int64, device="cuda")
+    lse = torch.empty(ops.attn_lse_numel(b, heads, sq), device="cuda")
+
+    def fwd(vv, pd):
+        out = torch.empty(b * sq, H, dtype=torch.bfloat16, device="cuda")
+        ops.attention_fwd(q, k, vv, out, lse, batch=b, heads=heads, sq=sq, sk=sk, d=d, p_drop=pd, site=7, seed=seed)
+        return out
+    out_d, out_0 = fwd(v, p), fwd(v, 0.0)
+    assert torch.equal(out_d, fwd(v, p))                              # same seed and site: same masks
+    rel = ((out_d.float() - out_0.float()).norm() / out_0.float().norm()).item()
+    assert 0.02 < rel < 0.6, rel                                       # dropout changed the output, but not its scale
+    # with v = ones the output is the kept probability mass / (1 - p): its mean is 1
+    ones = torch.ones_like(v)
+    assert abs(fwd(ones, p).float().mean().item() - 1.0) < 0.02
+    # dv is linear in dout through the dropped probabilities: <dout, fwd(dv_dir)> == <dv, dv_dir>
+    dout = _bf((b * sq, H), 14)
+    dq, dk, dv = (torch.empty_like(t) for t in (q, k, v))
+    out_d = fwd(v, p)
+    ops.attention_bwd(dout, q, k, v, lse, dq, dk, dv, batch=b, heads=heads, sq=sq, sk=sk, d=d, p_drop=p, site=7, seed=seed,
+                      out=out_d)
+    direction = _bf((b * sk, H), 15)
+    lhs = (dout.float() * fwd(direction, p).float()).sum().item()
+    rhs = (dv.float() * direction.float()).sum().item()
+    assert abs(lhs - rhs) <= 3e-2 * max(abs(lhs), abs(rhs)) + 1.0, (lhs, rhs)

@@ -158,3 +158,23 @@ def test_training_mode_dropout_runs_and_loss_is_finite():
         assert torch.isfinite(model.classifier[1].weight.grad).all()
     assert len(set(losses)) == 3, losses          # a new dropout mask every step (seed advances inside the graph)
     assert all(abs(l - 0.69) < 0.3 for l in losses)
+
+
+def test_257_regions_against_oracle_and_graph_replay():
+    """BASELINE config 4: 257 DINOv2 patch tokens as regions (blocked attention: 3 x 3 visual self-attention blocks, 3 key
+    blocks for tokens -> regions, 3 query blocks for regions -> tokens).  Logits, loss and every CE gradient against the
+    fp32 oracle; then the captured graphs reproduce the eager step."""
+    from multimodal_classification_b200 import selfcheck
+    cfg = vo.tiny_config()
+    selfcheck.compare_with_oracle(cfg, dict(batch=2, seq=64, regions=257, seed=9, with_visual_mask=True))
+    model = _model(cfg)
+    batch = {k: v.cuda() for k, v in vo.synthetic_batch(cfg, batch=2, seq=64, regions=257, seed=9).items()}
+    results = []
+    for it in range(3):
+        model.zero_grad(set_to_none=True)
+        out = model(**batch)
+        out["loss"].backward()
+        results.append((out["logits"].clone(), model.bert.encoder.v_layer[0].attention.self.query.weight.grad.clone(),
+                        model.bert.encoder.c_layer[0].biattention.key1.weight.grad.clone()))
+    for r in results[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(r, results[0]))
