@@ -13,7 +13,7 @@ loads from / into the reference extractor's.  CUDA only; there is no fallback.""
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Sequence, Tuple
+from typing import Sequence, Tuple
 
 import torch
 import torch.nn as nn

@@ -13,7 +13,6 @@ The whole trunk for one batch shape is captured in a CUDA graph.  There is no CP
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np

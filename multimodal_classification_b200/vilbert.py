@@ -11,7 +11,6 @@ Precision: fp32 master weights and gradients, bf16 weight shadows / activations,
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Any, Dict, List, Optional, Tuple
 

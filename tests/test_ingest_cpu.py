@@ -2,7 +2,6 @@
 decoding, bulk tokenisation, blob layout, epoch order) against tests/golden/ingest.npz, the batches the reference's own
 LMDBFeaturesDataset / PrecomputedFeaturesDataset + DataLoader produced (oracle/make_golden_ingest.py).  No kernel runs here:
 the device half (bf16 rounding, box normalisation) is covered by tests/test_ingest_gpu.py."""
-import os
 
 import numpy as np
 import pytest

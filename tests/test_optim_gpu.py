@@ -1,6 +1,5 @@
 """Fused clip + AdamW + shadow refresh against torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW (the reference's step,
 pipelines/model_training/nodes.py:757-760, 795-799) on the same gradients, fp32, three steps with a changing LR."""
-import copy
 
 import pytest
 import torch
