@@ -2,51 +2,22 @@
 and pinned memory are replaced by inert stand-ins and the one kernel by the oracle's arithmetic, so that slot hand-over,
 epoch restarts, short last batches, abandoned epochs and producer errors are covered without a GPU.  The real device path
 is tests/test_ingest_gpu.py."""
-import contextlib
 import pickle
 
 import numpy as np
 import pytest
 import torch
 
-from oracle import ingest_oracle as io
-
 from ingest_fixture import BS, F, G, KEYS, R, T, frame, golden_batches, store, tokenizer  # noqa: E402
-
-
-class _Event:
-    def record(self, stream=None):
-        pass
-
-    def synchronize(self):
-        pass
-
-
-class _Stream:
-    cuda_stream = 0
-
-    def wait_event(self, event):
-        pass
 
 
 @pytest.fixture
 def ingest_on_cpu(monkeypatch):
-    from multimodal_classification_b200 import ingest, ops
+    import cuda_standins
+    from multimodal_classification_b200 import ingest
     if torch.cuda.is_available():
         pytest.skip("stand-ins are for the GPU-less container")
-    for name, value in [("is_available", lambda: True), ("current_device", lambda: 0), ("set_device", lambda d: None),
-                        ("device", lambda d: contextlib.nullcontext()), ("stream", lambda s: contextlib.nullcontext()),
-                        ("current_stream", lambda d=None: _Stream()), ("Stream", _Stream), ("Event", _Event)]:
-        monkeypatch.setattr(torch.cuda, name, value)
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
-
-    def regions(features=None, features_bf16=None, boxes=None, spatial=None, box_div=1000.0, area_div=1e6, stream=None):
-        if features is not None:
-            features_bf16.copy_(features.to(torch.bfloat16))
-        if boxes is not None:
-            b = boxes.reshape(-1, boxes.shape[-1]).numpy()
-            spatial.copy_(torch.from_numpy(io.process_boxes(b, b.shape[0])).view(spatial.shape))
-    monkeypatch.setattr(ops, "lmdb_regions", regions)
+    cuda_standins.apply(monkeypatch.setattr)
     return ingest
 
 
@@ -119,3 +90,57 @@ def test_two_ranks_get_disjoint_equal_shards(ingest_on_cpu):
     assert not np.array_equal(seen[0], seen[1])
     with pytest.raises(ingest.VbError):
         ingest.FeatureStoreLoader(frame(), rec, tokenizer(), T, 2, device="cpu", rank=2, world_size=2)
+
+
+# ------------------------------------------------------------------------------------------------ two processes (gloo)
+def _rank_worker(rank, world, port, q):
+    import os
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import cuda_standins
+        from multimodal_classification_b200 import ingest
+        cuda_standins.apply(setattr)
+        rec = ingest.LMDBRecords(store().get, R, F)
+        train, val, _ = ingest.create_lmdb_dataloaders(frame(), frame().iloc[:5], frame().iloc[:2], batch_size=2, max_seq_length=T,
+                                                        device="cpu", tokenizer=tokenizer(), records=rec)
+        mine = np.concatenate([b["input_ids"].numpy() for b in train])
+        val_rows = sum(b["labels"].shape[0] for b in val)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        q.put((rank, (train.rank, train.world_size, val.world_size), len(train), mine.shape, val_rows,
+               [g.tobytes() for g in gathered]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_factories_shard_the_training_split_over_a_gloo_group():
+    """create_lmdb_dataloaders inside a world-size-2 process group: the training loaders take their rank from the group and
+    read disjoint, equally long shards of one permutation; validation stays whole on every rank."""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.is_available():
+        pytest.skip("stand-ins are for the GPU-less container")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [(0, 2, 1), (1, 2, 1)]
+    assert res[0][2] == res[1][2] == 3 and res[0][3] == res[1][3] == (6, T)      # 11 samples -> 6 per rank, drop_last keeps 3 x 2
+    assert res[0][4] == res[1][4] == 5
+    assert res[0][5] == res[1][5]                                                 # both ranks gathered the same shards
+    rows = np.concatenate([np.frombuffer(b, np.int64).reshape(-1, T) for b in res[0][5]])
+    all_ids = np.concatenate([b["input_ids"] for b in golden_batches("lmdb_seq")])
+    assert {r.tobytes() for r in rows} == {r.tobytes() for r in all_ids}          # together: every sample (one wrapped twice)
