@@ -57,3 +57,51 @@ def test_bilinear_concat_kernel_vs_interpolate():
         _lib.check(_lib.lib().vb_bilinear_concat(ptrs, layers, out.data_ptr(), b, grid, target, h, grid * grid * h, h, 0,
                                                  torch.cuda.current_stream().cuda_stream), "vb_bilinear_concat")
         assert torch.equal(out.float().cpu(), ref.to(torch.bfloat16).float())
+
+
+def test_oracle_identity_grid_keeps_every_patch_token():
+    """num_regions = the patch count (16 x 16 at 224 px): the reference's resize is the identity, the tail is a per-token MLP."""
+    from oracle import roi_oracle as ro
+    feats, sd = ro.seeded_fusion_inputs(seed=5, grid=16)
+    with torch.no_grad():
+        out = ro.dinov2_fusion_tail(feats, sd, 256)
+        fused = torch.cat(feats, -1)[0]
+        y = torch.nn.functional.linear(fused, sd["projection.0.weight"], sd["projection.0.bias"])
+        y = torch.nn.functional.gelu(torch.nn.functional.layer_norm(y, (2048,), sd["projection.1.weight"], sd["projection.1.bias"]))
+        want = torch.nn.functional.linear(y, sd["projection.3.weight"], sd["projection.3.bias"])
+    assert out.shape == (256, 2048) and torch.allclose(out, want, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_config4_all_patch_tokens_feed_the_encoder():
+    """BASELINE config 4 end to end: 4 layers x (CLS + 16 x 16 patch tokens) x 1024 -> concat -> projection -> 256 regions x
+    2048 + grid boxes -> two-stream encoder (blocked attention over 256 regions).  Tail against the oracle tail; encoder
+    against the oracle encoder on the tail's own output."""
+    from multimodal_classification_b200.dinov2_fusion import DINOv2FusionTail
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    from oracle import roi_oracle as ro
+    from oracle import vilbert_oracle as vo
+    feats, sd = ro.seeded_fusion_inputs(seed=5, grid=16)
+    tail = DINOv2FusionTail(num_layers=4, hidden_size=1024, output_dim=2048, num_regions=256, device="cuda")
+    tail.load_state_dict(sd, strict=True)
+    with_cls = [torch.cat([torch.zeros(1, 1, 1024), f], dim=1).repeat(2, 1, 1).cuda() for f in feats]
+    out, spatial = tail.fuse(with_cls, has_cls=True)
+    assert out.shape == (2, 256, 2048) and spatial.shape == (2, 256, 5)
+    with torch.no_grad():
+        ref = ro.dinov2_fusion_tail(feats, sd, 256).numpy()
+    err = np.abs(out[0].cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err <= 2e-2, err
+    assert np.array_equal(spatial[0].cpu().numpy(), ro.grid_spatial(256))
+    cfg = vo.tiny_config()
+    msd = vo.seeded_state_dict(cfg)
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(msd, strict=True)
+    model = model.cuda().eval()
+    batch = vo.synthetic_batch(cfg, batch=2, seq=32, regions=256, seed=3)
+    batch["visual_features"], batch["spatial_locations"] = out.cpu(), spatial.cpu()
+    with torch.no_grad():
+        got = model(**{k: v.cuda() for k, v in batch.items()})
+    want, _ = vo.loss_and_grads(msd, cfg, batch)
+    scale = want["logits"].abs().max().item()
+    assert (got["logits"].float().cpu() - want["logits"]).abs().max().item() <= 2e-2 * scale
+    assert abs(got["loss"].item() - want["loss"].item()) <= 1e-3
