@@ -221,9 +221,29 @@ def time_ingest(torch, dev, step, timed, steps, **loader_kw):
     ms = timed(ingest_step, steps)
     blob = loader._layout(B).nbytes
     del it
-    return {"value": B / (ms / steps * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
-            "h2d_bytes_per_step": int(blob), "d2h_bytes_per_step": 4, "loader_only_samples_per_sec": loader_only,
-            "source": f"{n_rec} pickled records ({R}x2048 fp32 features + {R}x4 boxes) in host memory, 1 producer thread, ring of 3"}
+    out = {"value": B / (ms / steps * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "h2d_bytes_per_step": int(blob), "d2h_bytes_per_step": 4, "loader_only_samples_per_sec": loader_only,
+           "source": f"{n_rec} pickled records ({R}x2048 fp32 features + {R}x4 boxes) in host memory, 1 producer thread, ring of 3"}
+    try:      # beside it: the reference's loader shape (per-sample Dataset + default collate + pin + copy), oracle port, one thread
+        from oracle import ingest_oracle as io
+        tok, ids = SyntheticTokenizer(), [str(i % n_rec) for i in range(rows)]
+
+        class PerSample:
+            def __call__(self, text, max_length, **kw):
+                e = tok([text], max_length)
+                return {k: v[0] for k, v in e.items()}
+        per_sample, done, t0 = PerSample(), 0, time.perf_counter()
+        while time.perf_counter() - t0 < 2.0:
+            samples = [io.lmdb_sample(ids[(done + j) % rows], "synthetic", 0, store.get, per_sample, T, R, 2048) for j in range(B)]
+            batch = {k: torch.from_numpy(v).pin_memory().to(dev, non_blocking=True) for k, v in io.collate(samples).items()}
+            done += B
+        torch.cuda.synchronize()
+        del batch
+        out["reference_style_loader_samples_per_sec"] = done / (time.perf_counter() - t0)
+        out["reference_style_loader"] = "oracle port of LMDBFeaturesDataset.__getitem__ + default collate + pin + H2D, 1 thread, same records"
+    except Exception as e:
+        out["reference_style_loader_error"] = repr(e)[:160]
+    return out
 
 
 def main():
