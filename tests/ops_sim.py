@@ -1,0 +1,284 @@
+"""CPU functional stand-ins for the kernel wrappers of multimodal_classification_b200/ops.py that the ViLBERT engine calls
+(dropout off), written from the semantics documented in include/vilbert_b200.h with plain torch fp32 arithmetic on the
+tensors the engine hands over (bf16 storage is kept: results are rounded into the engine's own buffers).  They let the
+engine's host schedule — which buffer feeds which kernel on which stream, the flat parameter / gradient layout, the fp32
+residual ring, the backward order — run against the oracle in the GPU-less container.  TEST INFRASTRUCTURE ONLY: nothing
+here is importable from the package, and the product path still refuses to run without CUDA."""
+import contextlib
+import math
+
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD = 0, 1, 2
+
+
+def _no_dropout(*ps):
+    assert all(p == 0.0 for p in ps), "the simulator covers the dropout-off configuration"
+
+
+def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, scale=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE,
+         preact=None, accumulate=False, block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False):
+    am = a.float().t() if a_mn_major else a.float()               # [M, K]
+    bm = b.float().t() if b_mn_major else b.float()               # [N, K]
+    v = am @ bm.t()
+    if scale is not None:
+        v = v * scale
+    if bias is not None:
+        v = v + bias
+    if preact is not None:
+        preact.copy_(v)
+    if aux_mode == AUX_ADD:
+        v = v + aux.float()
+    elif aux_mode == AUX_MUL_GELU_GRAD:
+        x = aux.float()
+        v = v * (0.5 * (1.0 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi))
+    if act == ACT_GELU:
+        v = F.gelu(v)
+    elif act == ACT_RELU:
+        v = F.relu(v)
+    elif act == ACT_TANH:
+        v = torch.tanh(v)
+    if accumulate:
+        assert out.dtype == torch.float32
+        out.add_(v)
+    else:
+        out.copy_(v)
+    return out
+
+
+def _ln_input(x, res, res32):
+    s = x.float()
+    if res32 is not None:
+        s = s + res32
+    elif res is not None:
+        s = s + res.float()
+    return s
+
+
+def layernorm_fwd(x, res, gamma, beta, y, mean, rstd, *, eps=1e-12, p_in=0.0, site_in=0, p_out=0.0, site_out=0, seed=None,
+                  res32=None, y32=None):
+    _no_dropout(p_in, p_out)
+    s = _ln_input(x, res, res32)
+    mu = s.mean(-1)
+    rs = torch.rsqrt(s.var(-1, unbiased=False) + eps)
+    v = (s - mu[:, None]) * rs[:, None] * gamma + beta
+    y.copy_(v)
+    if y32 is not None:
+        y32.copy_(v)
+    mean.copy_(mu)
+    rstd.copy_(rs)
+    return y
+
+
+def layernorm_bwd(dy, x, res, gamma, mean, rstd, *, dx=None, dres=None, dgamma=None, dbeta=None, dbias=None, eps=1e-12,
+                  p_in=0.0, site_in=0, p_out=0.0, site_out=0, seed=None, res32=None):
+    _no_dropout(p_in, p_out)
+    s = _ln_input(x, res, res32)
+    xhat = (s - mean[:, None]) * rstd[:, None]
+    g = dy.float()
+    gg = g * gamma
+    d = rstd[:, None] * (gg - gg.mean(-1, keepdim=True) - xhat * (gg * xhat).mean(-1, keepdim=True))
+    if dx is not None:
+        dx.copy_(d)
+    if dres is not None:
+        dres.copy_(d)
+    if dgamma is not None:
+        dgamma.add_((g * xhat).sum(0))
+    if dbeta is not None:
+        dbeta.add_(g.sum(0))
+    if dbias is not None:
+        dbias.add_(d.sum(0))
+
+
+def _emb_sum(ids, type_ids, word, pos, typ, b, t):
+    idx = ids.long()
+    e = word[idx] + (typ[type_ids.long()] if type_ids is not None else typ[0])
+    return e + pos[:t].repeat(b, 1)
+
+
+def embed_text_fwd(ids, type_ids, word, pos, typ, gamma, beta, y, mean, rstd, b, t, *, eps=1e-12, p_out=0.0, site_out=0,
+                   seed=None, y32=None):
+    _no_dropout(p_out)
+    s = _emb_sum(ids, type_ids, word, pos, typ, b, t)
+    mu = s.mean(-1)
+    rs = torch.rsqrt(s.var(-1, unbiased=False) + eps)
+    v = (s - mu[:, None]) * rs[:, None] * gamma + beta
+    y.copy_(v)
+    if y32 is not None:
+        y32.copy_(v)
+    mean.copy_(mu)
+    rstd.copy_(rs)
+    return y
+
+
+def embed_text_bwd(dy, ids, type_ids, word, pos, typ, gamma, mean, rstd, b, t, *, dword=None, dpos=None, dtype=None,
+                   dgamma=None, dbeta=None, eps=1e-12, p_out=0.0, site_out=0, seed=None):
+    _no_dropout(p_out)
+    s = _emb_sum(ids, type_ids, word, pos, typ, b, t)
+    xhat = (s - mean[:, None]) * rstd[:, None]
+    g = dy.float()
+    gg = g * gamma
+    d = rstd[:, None] * (gg - gg.mean(-1, keepdim=True) - xhat * (gg * xhat).mean(-1, keepdim=True))
+    if dword is not None:
+        keep = (ids != 0).float()[:, None]                       # padding_idx = 0 receives no gradient
+        dword.index_add_(0, ids.long(), d * keep)
+    if dpos is not None:
+        dpos[:t].add_(d.view(b, t, -1).sum(0))
+    if dtype is not None:
+        tt = type_ids.long() if type_ids is not None else torch.zeros_like(ids, dtype=torch.long)
+        dtype.index_add_(0, tt, d)
+    if dgamma is not None:
+        dgamma.add_((g * xhat).sum(0))
+    if dbeta is not None:
+        dbeta.add_(g.sum(0))
+
+
+def colsum(x, out):
+    out.add_(x.float().sum(0))
+    return out
+
+
+def cast_bf16(src, dst):
+    dst.copy_(src)
+    return dst
+
+
+def mask_bias(mask, out):
+    out.view(-1).copy_(((1.0 - mask.float()) * -10000.0).view(-1))
+    return out
+
+
+def i64_to_i32(src, dst, lo, hi, err_flag=None):
+    v = src.reshape(-1)
+    dst.copy_(torch.where((v < lo) | (v >= hi), torch.full_like(v, lo), v))
+    return dst
+
+
+def dropout(x, y, p, site, seed):
+    raise AssertionError("dropout kernel reached with dropout off")
+
+
+def seed_advance(seed):
+    pass
+
+
+def act_bwd(dy, y, dx, act):
+    yv = y.float()
+    dx.copy_(dy.float() * ((1.0 - yv * yv) if act == ACT_TANH else (yv > 0).float()))
+    return dx
+
+
+def loc_embed_fwd(loc, w, b, out):
+    out.copy_(loc @ w.t() + b)
+    return out
+
+
+def loc_embed_bwd(ds, loc, dw, db):
+    g = ds.float()
+    dw.add_(g.t() @ loc)
+    db.add_(g.sum(0))
+
+
+def cls_ce_fwd(h, w, bias, labels, logits, probs, loss):
+    z = h.float() @ w.t() + bias
+    logits.copy_(z)
+    probs.copy_(torch.softmax(z, -1))
+    loss.fill_(0.0 if labels is None else F.cross_entropy(z, labels.long()).item())
+
+
+def cls_ce_bwd(h, w, labels, probs, dloss, dlogits_ext, dw, db, dh):
+    bsz = probs.shape[0]
+    dz = dlogits_ext.clone() if dlogits_ext is not None else torch.zeros_like(probs)
+    if labels is not None:
+        dz = dz + dloss * (probs - F.one_hot(labels.long(), probs.shape[1]).float()) / bsz
+    dw.copy_(dz.t() @ h.float())
+    db.copy_(dz.sum(0))
+    dh.copy_(dz @ w)
+
+
+def _heads(x, batch, s, heads, d):
+    return x.float().reshape(batch, s, heads, d).permute(0, 2, 1, 3)
+
+
+def _probs(q, k, batch, heads, sq, sk, d, mask_bias_t, scale):
+    sc = _heads(q, batch, sq, heads, d) @ _heads(k, batch, sk, heads, d).transpose(-1, -2) * scale
+    if mask_bias_t is not None:
+        sc = sc + mask_bias_t.view(batch, 1, 1, sk)
+    return torch.softmax(sc, -1)
+
+
+def attention_fwd(q, k, v, out, lse, *, batch, heads, sq, sk, d, mask_bias=None, scale=None, p_drop=0.0, site=0, seed=None):
+    _no_dropout(p_drop)
+    scale = 1.0 / math.sqrt(d) if scale is None else scale
+    p = _probs(q, k, batch, heads, sq, sk, d, mask_bias, scale)
+    out.copy_((p @ _heads(v, batch, sk, heads, d)).permute(0, 2, 1, 3).reshape(batch * sq, heads * d))
+    return out
+
+
+def attention_bwd(dout, q, k, v, lse, dq, dk, dv, *, batch, heads, sq, sk, d, mask_bias=None, scale=None, p_drop=0.0, site=0,
+                  seed=None, out=None):
+    _no_dropout(p_drop)
+    scale = 1.0 / math.sqrt(d) if scale is None else scale
+    p = _probs(q, k, batch, heads, sq, sk, d, mask_bias, scale)
+    qh, kh, vh = _heads(q, batch, sq, heads, d), _heads(k, batch, sk, heads, d), _heads(v, batch, sk, heads, d)
+    do = _heads(dout, batch, sq, heads, d)
+    dp = do @ vh.transpose(-1, -2)
+    ds = p * (dp - (p * dp).sum(-1, keepdim=True)) * scale
+
+    def flat(t, s):
+        return t.permute(0, 2, 1, 3).reshape(batch * s, heads * d)
+    dq.copy_(flat(ds @ kh, sq))
+    dk.copy_(flat(ds.transpose(-1, -2) @ qh, sk))
+    dv.copy_(flat(p.transpose(-1, -2) @ do, sk))
+
+
+SIMULATED = ["gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "colsum", "cast_bf16", "mask_bias",
+             "i64_to_i32", "dropout", "seed_advance", "act_bwd", "loc_embed_fwd", "loc_embed_bwd", "cls_ce_fwd", "cls_ce_bwd",
+             "attention_fwd", "attention_bwd"]
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+    def wait_event(self, event):
+        pass
+
+    def record_event(self, event=None):
+        return event
+
+
+class _Event:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def wait(self, stream=None):
+        pass
+
+
+def install(monkeypatch):
+    """Route the engine's kernel wrappers to the stand-ins above and make the CUDA runtime objects it touches inert."""
+    from multimodal_classification_b200 import ops
+    here = globals()
+    for name in SIMULATED:
+        monkeypatch.setattr(ops, name, here[name])
+    main = _Stream()
+    for name, value in [("Stream", _Stream), ("Event", _Event), ("current_stream", lambda d=None: main),
+                        ("stream", lambda s: contextlib.nullcontext()), ("device", lambda d: contextlib.nullcontext()),
+                        ("synchronize", lambda d=None: None), ("is_current_stream_capturing", lambda: False)]:
+        monkeypatch.setattr(torch.cuda, name, value)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    monkeypatch.setenv("VB_NO_GRAPH", "1")
