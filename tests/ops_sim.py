@@ -145,6 +145,11 @@ def cast_bf16(src, dst):
     return dst
 
 
+def cast_f32(src, dst):
+    dst.copy_(src)
+    return dst
+
+
 def mask_bias(mask, out):
     out.view(-1).copy_(((1.0 - mask.float()) * -10000.0).view(-1))
     return out
@@ -234,7 +239,7 @@ def attention_bwd(dout, q, k, v, lse, dq, dk, dv, *, batch, heads, sq, sk, d, ma
     dv.copy_(flat(p.transpose(-1, -2) @ do, sk))
 
 
-SIMULATED = ["gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "colsum", "cast_bf16", "mask_bias",
+SIMULATED = ["gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "colsum", "cast_bf16", "cast_f32", "mask_bias",
              "i64_to_i32", "dropout", "seed_advance", "act_bwd", "loc_embed_fwd", "loc_embed_bwd", "cls_ce_fwd", "cls_ce_bwd",
              "attention_fwd", "attention_bwd"]
 
@@ -282,3 +287,16 @@ def install(monkeypatch):
         monkeypatch.setattr(torch.cuda, name, value)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     monkeypatch.setenv("VB_NO_GRAPH", "1")
+
+
+class PlainPatch:
+    """monkeypatch-shaped setter for spawned worker processes (no undo needed there)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+    @staticmethod
+    def setenv(name, value):
+        import os
+        os.environ[name] = value

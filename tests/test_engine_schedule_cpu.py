@@ -51,3 +51,68 @@ def test_engine_schedule_matches_oracle(simulated, batch_kw):
         cos = float((g @ r) / (g.norm() * r.norm() + 1e-30))
         worst = min(worst, (cos, k))
     assert worst[0] >= 0.97, worst
+
+
+# ------------------------------------------------------------------------------------------------ data parallel (gloo)
+def _dp_worker(rank, world, port, compress, q):
+    import os
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ops_sim
+        from multimodal_classification_b200 import ddp
+        from multimodal_classification_b200.vilbert import ViLBERTForClassification
+        ops_sim.install(ops_sim.PlainPatch)
+        ddp.FLUSH_BYTES = 1 << 20                       # several grouped exchanges inside one backward pass
+        cfg = vo.tiny_config()
+        sd = vo.seeded_state_dict(cfg)
+        model = ViLBERTForClassification(cfg, num_labels=2)
+        model.load_state_dict(sd, strict=True)
+        model.eval()
+        ddp.attach(model, dist.group.WORLD, compress=compress)
+        batches = [vo.synthetic_batch(cfg, batch=2, seq=16, regions=8, seed=10 + r) for r in range(world)]
+        out = model(**batches[rank])
+        out["loss"].backward()
+        refs = [vo.loss_and_grads(sd, cfg, b)[1] for b in batches]
+        worst, worst_rel = (1.0, ""), 0.0
+        for k, p in model.named_parameters():
+            if refs[0][k] is None or (".key" in k and k.endswith(".bias")):
+                continue
+            want = torch.stack([r[k] for r in refs]).mean(0).flatten().double()
+            g = p.grad.flatten().double()
+            worst = min(worst, (float((g @ want) / (g.norm() * want.norm() + 1e-30)), k))
+            worst_rel = max(worst_rel, float(abs(g.norm() - want.norm()) / (want.norm() + 1e-30)))
+        digest = float(sum(p.grad.double().sum() for p in model.parameters() if p.grad is not None))
+        q.put((rank, worst, worst_rel, digest))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("compress", [None, "bf16"])
+def test_data_parallel_backward_averages_gradients_over_gloo(compress):
+    """Two ranks, different batches, the engine's own bucket exchange inside backward (grouped all-reduces over the flat
+    gradient buffer, fp32 and bf16-compressed): every rank ends with the mean of the two single-rank oracle gradients."""
+    import socket
+    import torch.multiprocessing as mp
+    if torch.cuda.is_available():
+        pytest.skip("the stand-ins are for the GPU-less container")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, compress, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, worst, worst_rel, digest in res:
+        assert worst[0] >= 0.97, (rank, worst)
+        assert worst_rel <= 0.2, (rank, worst_rel)
+    assert abs(res[0][3] - res[1][3]) <= 1e-6 * max(1.0, abs(res[0][3]))       # both ranks hold the same averaged gradients
