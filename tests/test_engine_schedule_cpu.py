@@ -53,6 +53,76 @@ def test_engine_schedule_matches_oracle(simulated, batch_kw):
     assert worst[0] >= 0.97, worst
 
 
+def _close_grads(model, ref_grads, factor=1.0):
+    for k, p in model.named_parameters():
+        r = ref_grads[k]
+        if r is None or (".key" in k and k.endswith(".bias")):
+            continue
+        g, r = p.grad.flatten().double(), r.flatten().double() * factor
+        assert float((g @ r) / (g.norm() * r.norm() + 1e-30)) >= 0.97, k
+        assert abs(float(g.norm()) - float(r.norm())) <= 0.15 * float(r.norm()) + 1e-6, k
+
+
+def test_no_grad_frozen_layers_and_gradient_accumulation(simulated):
+    """Host paths around the schedule: the no_grad forward equals the training-graph forward; frozen text layers receive no
+    gradient while the rest is unchanged; a second backward without zeroing accumulates (2x the oracle gradient)."""
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    cfg = vo.tiny_config()
+    sd = vo.seeded_state_dict(cfg)
+    batch = vo.synthetic_batch(cfg, batch=2, seq=16, regions=8, seed=21)
+    _, ref_grads = vo.loss_and_grads(sd, cfg, batch)
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        plain = model(**batch)
+    out = model(**batch)
+    assert torch.equal(plain["logits"], out["logits"]) and not plain["logits"].requires_grad and out["loss"].requires_grad
+    out["loss"].backward()
+    _close_grads(model, ref_grads)
+    model(**batch)["loss"].backward()                    # no zero_grad in between: gradients add up
+    _close_grads(model, ref_grads, factor=2.0)
+    model.zero_grad(set_to_none=True)
+    model.freeze_bert_layers(2)
+    model(**batch)["loss"].backward()
+    frozen = [k for k, p in model.named_parameters() if not p.requires_grad]
+    assert frozen and all(k.startswith(("bert.embeddings.", "bert.encoder.layer.0.", "bert.encoder.layer.1.")) for k in frozen)
+    assert all(dict(model.named_parameters())[k].grad is None for k in frozen)
+    for p in model.parameters():
+        p.requires_grad_(True)
+
+
+@pytest.mark.parametrize("env", [{"VB_ONE_STREAM": "1"}, {"VB_BF16_RESIDUAL": "1"}, {"VB_NO_SIDE": "1"}])
+def test_engine_switches_keep_the_result(simulated, monkeypatch, env):
+    """The engine's scheduling switches (one stream, no side streams, bf16 residual stream) change where and in which
+    precision kernels run, not what is computed."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg = vo.tiny_config()
+    model, out, ref_out, ref_grads = _run(cfg, dict(batch=2, seq=16, regions=8, seed=4))
+    assert (out["logits"].float() - ref_out["logits"]).abs().max().item() <= 2e-2 * ref_out["logits"].abs().max().item()
+    _close_grads(model, ref_grads)
+
+
+def test_more_than_128_regions_and_mixed_input_dtypes(simulated):
+    """130 regions (the log-sum-exp buffers grow to two query blocks), int32 ids, float masks, bf16 features."""
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    cfg = vo.tiny_config()
+    sd = vo.seeded_state_dict(cfg)
+    batch = vo.synthetic_batch(cfg, batch=2, seq=12, regions=130, seed=8, with_visual_mask=True)
+    ref_out, _ = vo.loss_and_grads(sd, cfg, batch)
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    mixed = dict(batch)
+    mixed["input_ids"] = batch["input_ids"].int()
+    mixed["attention_mask"] = batch["attention_mask"].float()
+    mixed["visual_features"] = batch["visual_features"].to(torch.bfloat16)
+    with torch.no_grad():
+        out = model(**mixed)
+    assert (out["logits"].float() - ref_out["logits"]).abs().max().item() <= 2e-2 * ref_out["logits"].abs().max().item()
+
+
 # ------------------------------------------------------------------------------------------------ data parallel (gloo)
 def _dp_worker(rank, world, port, compress, q):
     import os
