@@ -239,6 +239,63 @@ def attention_bwd(dout, q, k, v, lse, dq, dk, dv, *, batch, heads, sq, sk, d, ma
     dv.copy_(flat(p.transpose(-1, -2) @ do, sk))
 
 
+# ------------------------------------------------------------------------------------------------ RoI / grid feature stage
+def stem_im2col(img, out, kh=7, kw=7, stride=2, pad=3):
+    n, c, h, w = img.shape
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    cols = F.unfold(img, (kh, kw), padding=pad, stride=stride).view(n, c, kh * kw, ho * wo).permute(0, 3, 2, 1)
+    out.zero_()
+    out[:, : kh * kw * c].copy_(cols.reshape(n * ho * wo, kh * kw * c))          # column (ky*kw + kx)*3 + ci, zero padded
+    return out
+
+
+def im2col_nhwc(x, out, kh, kw, stride, pad):
+    n, h, w, c = x.shape
+    ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    cols = F.unfold(x.float().permute(0, 3, 1, 2), (kh, kw), padding=pad, stride=stride)
+    out.copy_(cols.view(n, c, kh * kw, ho * wo).permute(0, 3, 2, 1).reshape(n * ho * wo, kh * kw * c))
+    return out
+
+
+def maxpool_nhwc(x, out, k=3, stride=2, pad=1):
+    out.copy_(F.max_pool2d(x.float().permute(0, 3, 1, 2), k, stride, pad).permute(0, 2, 3, 1))
+    return out
+
+
+def roi_pool_nhwc(x, rois, out, spatial_scale, argmax=None):
+    import torchvision
+    r, ph, pw, c = out.shape
+    out.copy_(torchvision.ops.roi_pool(x.float().permute(0, 3, 1, 2).contiguous(), rois, (ph, pw), spatial_scale).permute(0, 2, 3, 1))
+    return out
+
+
+def roi_align_nhwc(x, rois, out, spatial_scale, sampling_ratio=2, aligned=False):
+    import torchvision
+    r, ph, pw, c = out.shape
+    out.copy_(torchvision.ops.roi_align(x.float().permute(0, 3, 1, 2).contiguous(), rois, (ph, pw), spatial_scale, sampling_ratio,
+                                        aligned).permute(0, 2, 3, 1))
+    return out
+
+
+def avgpool_nhwc(x, out):
+    out.copy_(x.float().mean(1))
+    return out
+
+
+def box_area_score(boxes, img_w, img_h, scores, target=0.15):
+    w = (boxes[:, 2] - boxes[:, 0]) / img_w
+    h = (boxes[:, 3] - boxes[:, 1]) / img_h
+    scores.copy_(1.0 - torch.abs(w * h - target))
+    return scores
+
+
+def nms(boxes, scores, iou_threshold):
+    import torchvision
+    return torchvision.ops.nms(boxes, scores, iou_threshold)
+
+
+ROI_SIMULATED = ["stem_im2col", "im2col_nhwc", "maxpool_nhwc", "roi_pool_nhwc", "roi_align_nhwc", "avgpool_nhwc", "box_area_score",
+                 "nms"]
 SIMULATED = ["gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "colsum", "cast_bf16", "cast_f32", "mask_bias",
              "i64_to_i32", "dropout", "seed_advance", "act_bwd", "loc_embed_fwd", "loc_embed_bwd", "cls_ce_fwd", "cls_ce_bwd",
              "attention_fwd", "attention_bwd"]
@@ -278,7 +335,7 @@ def install(monkeypatch):
     """Route the engine's kernel wrappers to the stand-ins above and make the CUDA runtime objects it touches inert."""
     from multimodal_classification_b200 import ops
     here = globals()
-    for name in SIMULATED:
+    for name in SIMULATED + ROI_SIMULATED:
         monkeypatch.setattr(ops, name, here[name])
     main = _Stream()
     for name, value in [("Stream", _Stream), ("Event", _Event), ("current_stream", lambda d=None: main),
