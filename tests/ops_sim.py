@@ -357,3 +357,22 @@ class PlainPatch:
     def setenv(name, value):
         import os
         os.environ[name] = value
+
+
+def install_device_shims(monkeypatch):
+    """For modules that move themselves or allocate with an explicit "cuda" device: keep everything on the CPU."""
+    orig_mto, orig_tto = torch.nn.Module.to, torch.Tensor.to
+
+    def is_cuda_arg(a):
+        return bool(a) and isinstance(a[0], (str, torch.device)) and str(a[0]).startswith("cuda")
+    monkeypatch.setattr(torch.nn.Module, "to", lambda self, *a, **k: self if is_cuda_arg(a) else orig_mto(self, *a, **k))
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: self if is_cuda_arg(a) else orig_tto(self, *a, **k))
+
+    def on_cpu(fn):
+        def wrapped(*a, **k):
+            if "device" in k and str(k["device"]).startswith("cuda"):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return wrapped
+    for name in ("zeros", "empty", "arange", "tensor", "full"):
+        monkeypatch.setattr(torch, name, on_cpu(getattr(torch, name)))

@@ -105,3 +105,57 @@ def test_config4_all_patch_tokens_feed_the_encoder():
     scale = want["logits"].abs().max().item()
     assert (got["logits"].float().cpu() - want["logits"]).abs().max().item() <= 2e-2 * scale
     assert abs(got["loss"].item() - want["loss"].item()) <= 1e-3
+
+
+def test_fusion_tail_host_logic_on_the_cpu(monkeypatch):
+    """DINOv2FusionTail.fuse in the GPU-less container: its two direct C-ABI calls (vb_bilinear_concat, vb_gelu_bf16) are
+    replaced by numpy restatements working through the pointers / strides fuse() passes, the GEMM and LayerNorm wrappers by
+    tests/ops_sim.py.  Against the reference-produced fixture, with and without the CLS token, batch of two."""
+    import ctypes as C
+    import torch.nn.functional as F
+    if torch.cuda.is_available():
+        pytest.skip("the stand-ins are for the GPU-less container")
+    import ops_sim
+    from multimodal_classification_b200 import _lib
+    from oracle import roi_oracle as ro
+
+    class FakeLib:
+        def vb_bilinear_concat(self, layers, n_layers, out, batch, grid, target, h, batch_stride, token_stride, first_token, stream):
+            cols = []
+            for l in range(n_layers):
+                n = (batch - 1) * batch_stride + (first_token + grid * grid) * token_stride
+                raw = np.ctypeslib.as_array((C.c_float * n).from_address(layers[l]))
+                x = torch.from_numpy(np.stack([raw[b * batch_stride + first_token * token_stride:][: grid * grid * token_stride]
+                                               .reshape(grid * grid, token_stride)[:, :h] for b in range(batch)]))
+                r = F.interpolate(x.permute(0, 2, 1).reshape(batch, h, grid, grid), size=(target, target), mode="bilinear",
+                                  align_corners=False)
+                cols.append(r.permute(0, 2, 3, 1).reshape(batch * target * target, h))
+            bits = torch.cat(cols, -1).to(torch.bfloat16).contiguous().view(torch.int16).numpy().view(np.uint16)
+            np.ctypeslib.as_array((C.c_uint16 * bits.size).from_address(out))[:] = bits.reshape(-1)
+            return 0
+
+        def vb_gelu_bf16(self, x, y, n, stream):
+            raw = np.ctypeslib.as_array((C.c_uint16 * n).from_address(x))
+            v = torch.from_numpy((raw.astype(np.uint32) << 16).view(np.float32).copy())
+            np.ctypeslib.as_array((C.c_uint16 * n).from_address(y))[:] = \
+                F.gelu(v).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+            return 0
+
+        def vb_last_error(self):
+            return b""
+
+    ops_sim.install(monkeypatch)
+    ops_sim.install_device_shims(monkeypatch)
+    monkeypatch.setattr(_lib, "lib", lambda: FakeLib())
+    from multimodal_classification_b200.dinov2_fusion import DINOv2FusionTail
+    feats, sd = ro.seeded_fusion_inputs()
+    tail = DINOv2FusionTail(num_layers=4, hidden_size=1024, output_dim=2048, num_regions=36, device="cuda")
+    tail.load_state_dict(sd, strict=True)
+    out, spatial = tail.fuse(feats)
+    ref = G["projected"]
+    assert out.shape == (1, 36, 2048) and np.array_equal(spatial[0].numpy(), G["spatial"])
+    assert np.abs(out[0].numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
+    with_cls = [torch.cat([torch.full((1, 1, 1024), 7.0), f], dim=1).repeat(2, 1, 1).contiguous() for f in feats]
+    out2, _ = tail.fuse(with_cls, has_cls=True)
+    # (CPU BLAS accumulates differently for 72 and 36 rows; the bf16 intermediates turn that into 1-ulp flips)
+    assert out2.shape == (2, 36, 2048) and torch.allclose(out2[0], out[0], atol=5e-3) and torch.allclose(out2[1], out2[0], atol=5e-3)

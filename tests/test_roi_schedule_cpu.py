@@ -14,20 +14,7 @@ def simulated(monkeypatch):
         pytest.skip("the stand-ins are for the GPU-less container")
     import ops_sim
     ops_sim.install(monkeypatch)
-    orig_to = torch.nn.Module.to
-    monkeypatch.setattr(torch.nn.Module, "to", lambda self, *a, **k: self if a and str(a[0]).startswith("cuda") else orig_to(self, *a, **k))
-    orig_tto = torch.Tensor.to
-    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: self if a and isinstance(a[0], (str, torch.device)) and str(a[0]).startswith("cuda") else orig_tto(self, *a, **k))
-    real_zeros, real_arange, real_tensor = torch.zeros, torch.arange, torch.tensor
-
-    def on_cpu(fn):
-        def wrapped(*a, **k):
-            if "device" in k and str(k["device"]).startswith("cuda"):
-                k["device"] = "cpu"
-            return fn(*a, **k)
-        return wrapped
-    for name in ("zeros", "empty", "arange", "tensor", "full"):
-        monkeypatch.setattr(torch, name, on_cpu(getattr(torch, name)))
+    ops_sim.install_device_shims(monkeypatch)
     # the backbone refuses CPU weights (product behaviour, tested in test_roi_gpu.py::test_cpu_device_is_refused); here the
     # same trunk cache is used without that check
     from multimodal_classification_b200 import resnet152_roi as rr
