@@ -21,6 +21,7 @@ from . import _lib, ops
 from ._lib import VbError
 
 CO_ATTENTION_TEXT_LAYERS = (1, 3, 5, 7, 9, 11)  # reference :457
+V_POS_KEY = "bert.v_embeddings.position_embeddings.weight"   # only the vilbert_core surface has it
 
 
 def get_facebook_vilbert_config() -> Dict[str, Any]:
@@ -146,7 +147,8 @@ class _FlatParams:
 
     def __init__(self, model: "ViLBERTForClassification", device):
         cfg = model.config
-        named = dict(model.named_parameters())
+        # a sibling surface (vilbert_core.py) hands its parameters over under THIS layout's names
+        named = dict(getattr(model, "_engine_named_parameters", model.named_parameters)())
         order_w: List[str] = []
         order_s: List[str] = []
 
@@ -182,6 +184,8 @@ class _FlatParams:
             lin(p + ".t_intermediate.dense"); lin(p + ".t_output.dense"); ln(p + ".t_output.LayerNorm")
         lin("bert.v_embeddings.image_embeddings")
         lin("bert.t_pooler.dense"); lin("bert.v_pooler.dense"); lin("classifier.1")
+        if V_POS_KEY in named:      # learned region-position table (vilbert_core.py:436): read through a one-hot GEMM operand
+            order_w.append(V_POS_KEY)
         order_s += ["bert.v_embeddings.image_location_embeddings.weight", "bert.v_embeddings.image_location_embeddings.bias",
                     "bert.v_embeddings.LayerNorm.weight", "bert.v_embeddings.LayerNorm.bias",
                     "classifier.4.weight", "classifier.4.bias",
@@ -191,7 +195,7 @@ class _FlatParams:
         used = set(order_w) | set(order_s)
         self.order_w = order_w
         order_u = [k for k in named if k not in used]
-        assert all("q_dense" in k for k in order_u), order_u
+        assert all("q_dense" in k or k.startswith("unused.") for k in order_u), order_u
 
         self.offsets: Dict[str, int] = {}
         off = 0
@@ -317,6 +321,20 @@ class _Plan:
         self.loss = self.buf("out.loss", (1,), f32)
         self.dloss = self.buf("in.dloss", (1,), f32)
         self.dlogits = self.buf("in.dlogits", (B, self.C), f32)
+        # constant one-hot GEMM operands of the vilbert_core surface: region index (position table) and sample index (mean pool)
+        self.onehot_r = self.onehot_b = self.inv_r = None
+        if V_POS_KEY in eng.flat.named:
+            if R > eng.flat.named[V_POS_KEY].shape[0]:
+                raise VbError(f"{R} regions exceed the region-position table ({eng.flat.named[V_POS_KEY].shape[0]} rows)")
+            rp = (R + 7) // 8 * 8
+            self.onehot_r = self.buf("const.onehot_r", (self.Mv, rp))
+            self.onehot_r.view(B, R, rp)[:, torch.arange(R), torch.arange(R)] = 1.0
+        if cfg.get("v_pool", "first") == "mean":
+            bp = (B + 7) // 8 * 8
+            self.onehot_b = self.buf("const.onehot_b", (self.Mv, bp))
+            self.onehot_b.view(B, R, bp)[torch.arange(B), :, torch.arange(B)] = 1.0
+            self.inv_r = self.buf("const.inv_r", (cfg["v_hidden_size"],), f32)
+            self.inv_r.fill_(1.0 / R)
 
     def buf(self, name, shape, dtype=torch.bfloat16) -> torch.Tensor:
         t = self.bufs.get(name)
@@ -568,8 +586,13 @@ class _Engine:
             loc = pl.buf("vemb.loc", (Mv, Hv))
             ops.loc_embed_fwd(pl.loc, f.m(ve + ".image_location_embeddings.weight").view(Hv, -1),
                               f.m(ve + ".image_location_embeddings.bias"), loc)
+            if pl.onehot_r is not None:     # + position_embeddings[region]  (vilbert_core.py:470-476)
+                res = pl.buf("vemb.res", (Mv, Hv))
+                ops.gemm(pl.onehot_r[:, :R], f.w(V_POS_KEY)[:R], res, b_mn_major=True, aux=loc, aux_mode=ops.AUX_ADD)
+                loc = res
             v = pl.buf("vemb.v", (Mv, Hv))
             sv["vemb_ln"] = self._ln(pl, img, loc, ve + ".LayerNorm", v, "vemb.ln", p_out=pvh)
+            sv["vemb_res"] = loc
 
         c = 0
         for i in range(cfg["num_hidden_layers"]):
@@ -587,20 +610,27 @@ class _Engine:
         pooled = pl.buf("head.pooled", (B, bi + Hv))
         ops.gemm(t.view(B, T * H)[:, :H], f.w("bert.t_pooler.dense.weight"), pooled[:, :bi],
                  bias=f.m("bert.t_pooler.dense.bias"), act=ops.ACT_TANH)
-        ops.gemm(v.view(B, R * Hv)[:, :Hv], f.w("bert.v_pooler.dense.weight"), pooled[:, bi:],
+        if pl.onehot_b is not None:         # mean over the regions (vilbert_core.py:581) instead of the first region (:404-408)
+            vmean32 = pl.buf("head.vmean32", (B, Hv), torch.float32)
+            ops.avgpool_nhwc(v.view(B, R, Hv), vmean32)
+            v_in = ops.cast_bf16(vmean32, pl.buf("head.vmean", (B, Hv)))
+        else:
+            v_in = v.view(B, R * Hv)[:, :Hv]
+        ops.gemm(v_in, f.w("bert.v_pooler.dense.weight"), pooled[:, bi:],
                  bias=f.m("bert.v_pooler.dense.bias"), act=ops.ACT_TANH)
         sv["head_site"] = self._next_site()
+        pc = cfg.get("classifier_dropout", 0.1)
         pooled_d = pooled
         if pl.dropout:
-            pooled_d = ops.dropout(pooled, pl.buf("head.pooled_d", (B, bi + Hv)), 0.1, sv["head_site"], self.seed)
+            pooled_d = ops.dropout(pooled, pl.buf("head.pooled_d", (B, bi + Hv)), pc, sv["head_site"], self.seed)
         hid = pl.buf("head.hid", (B, bi))
         ops.gemm(pooled_d, f.w("classifier.1.weight"), hid, bias=f.m("classifier.1.bias"), act=ops.ACT_RELU)
         hid_d = hid
         if pl.dropout:
-            hid_d = ops.dropout(hid, pl.buf("head.hid_d", (B, bi)), 0.1, sv["head_site"] + 1, self.seed)
+            hid_d = ops.dropout(hid, pl.buf("head.hid_d", (B, bi)), pc, sv["head_site"] + 1, self.seed)
         ops.cls_ce_fwd(hid_d, f.m("classifier.4.weight").view(pl.C, bi), f.m("classifier.4.bias"), pl.labels, pl.logits,
                        pl.probs, pl.loss)
-        sv.update(t_final=t, v_final=v, pooled=pooled, pooled_d=pooled_d, hid=hid, hid_d=hid_d)
+        sv.update(t_final=t, v_final=v, v_pool_in=v_in, pooled=pooled, pooled_d=pooled_d, hid=hid, hid_d=hid_d)
 
     def _co_layer_fwd(self, pl, c, v, t, s_t, s_v):
         """CoAttentionLayer.forward (reference :377-394): BiAttention :253-294, BiOutput :324-338, two FFNs."""
@@ -699,20 +729,25 @@ class _Engine:
                        f.g("classifier.4.weight"), f.g("classifier.4.bias"), g_hid_d)
         g_hid = g_hid_d
         if pl.dropout:
-            g_hid = ops.dropout(g_hid_d, pl.buf("g.hid", (B, bi)), 0.1, sv["head_site"] + 1, self.seed)
+            g_hid = ops.dropout(g_hid_d, pl.buf("g.hid", (B, bi)), cfg.get("classifier_dropout", 0.1), sv["head_site"] + 1, self.seed)
         g_hid_pre = ops.act_bwd(g_hid, sv["hid"], pl.buf("g.hid_pre", (B, bi)), ops.ACT_RELU)
         g_pooled_d = pl.buf("g.pooled_d", (B, bi + Hv))
         self._linear_bwd(g_hid_pre, sv["pooled_d"], "classifier.1.weight", dx=g_pooled_d)
         g_pooled = g_pooled_d
         if pl.dropout:
-            g_pooled = ops.dropout(g_pooled_d, pl.buf("g.pooled", (B, bi + Hv)), 0.1, sv["head_site"], self.seed)
+            g_pooled = ops.dropout(g_pooled_d, pl.buf("g.pooled", (B, bi + Hv)), cfg.get("classifier_dropout", 0.1), sv["head_site"], self.seed)
         g_pool_pre = ops.act_bwd(g_pooled, sv["pooled"], pl.buf("g.pool_pre", (B, bi + Hv)), ops.ACT_TANH)
         s_v.wait_stream(s_t)
         self._linear_bwd(g_pool_pre[:, :bi], sv["t_final"].view(B, T * H)[:, :H], "bert.t_pooler.dense.weight",
                          dx=dy_t[0].view(B, T * H)[:, :H])
         with torch.cuda.stream(s_v):
-            self._linear_bwd(g_pool_pre[:, bi:], sv["v_final"].view(B, R * Hv)[:, :Hv], "bert.v_pooler.dense.weight",
-                             dx=dy_v[0].view(B, R * Hv)[:, :Hv])
+            if pl.onehot_b is not None:     # mean pool: every region receives dpooled / R (one-hot GEMM with a column scale)
+                g_vmean = pl.buf("g.vmean", (B, Hv))
+                self._linear_bwd(g_pool_pre[:, bi:], sv["v_pool_in"], "bert.v_pooler.dense.weight", dx=g_vmean)
+                ops.gemm(pl.onehot_b[:, :B], g_vmean, dy_v[0], b_mn_major=True, scale=pl.inv_r)
+            else:
+                self._linear_bwd(g_pool_pre[:, bi:], sv["v_pool_in"], "bert.v_pooler.dense.weight",
+                                 dx=dy_v[0].view(B, R * Hv)[:, :Hv])
 
         # encoder, reversed
         it_, iv_ = 0, 0   # which ping/pong buffer currently holds the incoming gradient
@@ -738,9 +773,13 @@ class _Engine:
         with torch.cuda.stream(s_v):
             ve = "bert.v_embeddings"
             g_s = pl.buf("g.vemb_s", (Mv, Hv))
-            self._ln_bwd(pl, dy_v[iv_], pl.bufs["vemb.img"], pl.bufs["vemb.loc"], ve + ".LayerNorm", sv["vemb_ln"], dx=g_s,
+            self._ln_bwd(pl, dy_v[iv_], pl.bufs["vemb.img"], sv["vemb_res"], ve + ".LayerNorm", sv["vemb_ln"], dx=g_s,
                          dres=None, bias_key=ve + ".image_embeddings.bias", p_out=pvh)
             self._linear_bwd(g_s, pl.feat, ve + ".image_embeddings.weight", bias_grad=False)
+            if pl.onehot_r is not None:     # d position table = onehot^T g_s: the ordinary weight-gradient contraction
+                n_pos = f.named[V_POS_KEY].shape[0]
+                ops.gemm(pl.onehot_r[:, :R], g_s, f.g(V_POS_KEY, shape=(n_pos, Hv), numel=n_pos * Hv)[:R], a_mn_major=True,
+                         b_mn_major=True, d_streamed=True)
             ops.loc_embed_bwd(g_s, pl.loc, f.g(ve + ".image_location_embeddings.weight"),
                               f.g(ve + ".image_location_embeddings.bias"))
         e = "bert.embeddings"
