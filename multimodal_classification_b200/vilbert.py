@@ -329,7 +329,7 @@ class _Plan:
             rp = (R + 7) // 8 * 8
             self.onehot_r = self.buf("const.onehot_r", (self.Mv, rp))
             self.onehot_r.view(B, R, rp)[:, torch.arange(R), torch.arange(R)] = 1.0
-        if cfg.get("v_pool", "first") == "mean":
+        if cfg.get("_v_pool", "first") == "mean":
             bp = (B + 7) // 8 * 8
             self.onehot_b = self.buf("const.onehot_b", (self.Mv, bp))
             self.onehot_b.view(B, R, bp)[torch.arange(B), :, torch.arange(B)] = 1.0
@@ -619,7 +619,7 @@ class _Engine:
         ops.gemm(v_in, f.w("bert.v_pooler.dense.weight"), pooled[:, bi:],
                  bias=f.m("bert.v_pooler.dense.bias"), act=ops.ACT_TANH)
         sv["head_site"] = self._next_site()
-        pc = cfg.get("classifier_dropout", 0.1)
+        pc = cfg.get("_classifier_dropout", 0.1)
         pooled_d = pooled
         if pl.dropout:
             pooled_d = ops.dropout(pooled, pl.buf("head.pooled_d", (B, bi + Hv)), pc, sv["head_site"], self.seed)
@@ -729,13 +729,13 @@ class _Engine:
                        f.g("classifier.4.weight"), f.g("classifier.4.bias"), g_hid_d)
         g_hid = g_hid_d
         if pl.dropout:
-            g_hid = ops.dropout(g_hid_d, pl.buf("g.hid", (B, bi)), cfg.get("classifier_dropout", 0.1), sv["head_site"] + 1, self.seed)
+            g_hid = ops.dropout(g_hid_d, pl.buf("g.hid", (B, bi)), cfg.get("_classifier_dropout", 0.1), sv["head_site"] + 1, self.seed)
         g_hid_pre = ops.act_bwd(g_hid, sv["hid"], pl.buf("g.hid_pre", (B, bi)), ops.ACT_RELU)
         g_pooled_d = pl.buf("g.pooled_d", (B, bi + Hv))
         self._linear_bwd(g_hid_pre, sv["pooled_d"], "classifier.1.weight", dx=g_pooled_d)
         g_pooled = g_pooled_d
         if pl.dropout:
-            g_pooled = ops.dropout(g_pooled_d, pl.buf("g.pooled", (B, bi + Hv)), cfg.get("classifier_dropout", 0.1), sv["head_site"], self.seed)
+            g_pooled = ops.dropout(g_pooled_d, pl.buf("g.pooled", (B, bi + Hv)), cfg.get("_classifier_dropout", 0.1), sv["head_site"], self.seed)
         g_pool_pre = ops.act_bwd(g_pooled, sv["pooled"], pl.buf("g.pool_pre", (B, bi + Hv)), ops.ACT_TANH)
         s_v.wait_stream(s_t)
         self._linear_bwd(g_pool_pre[:, :bi], sv["t_final"].view(B, T * H)[:, :H], "bert.t_pooler.dense.weight",

@@ -8,8 +8,8 @@ Structurally this model IS the Facebook-architecture model with every width set 
 64) plus three differences, which ``vilbert._Engine`` switches on from the configuration / parameter set it is handed:
 
 * a learned region-position table in the visual embedding (``V_POS_KEY``; read through a one-hot GEMM operand);
-* the visual stream is mean-pooled before its pooler (``v_pool = "mean"``);
-* classifier dropout 0.5 (``classifier_dropout``).
+* the visual stream is mean-pooled before its pooler (``_v_pool = "mean"``);
+* classifier dropout 0.5 (``_classifier_dropout``).
 
 ``BertConnectionLayer`` (two cross-attentions, each with its own output dense + LayerNorm on the query's residual, then one
 FFN per stream; vilbert_core.py:271-330) is the engine's co-attention block under other names: the projections applied to the
@@ -24,7 +24,7 @@ CUDA only, no fall-back.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Iterator, Optional, Tuple
+from typing import Any, Dict, Iterator, Tuple
 
 import torch
 import torch.nn as nn
@@ -117,7 +117,7 @@ class ViLBERTForClassification(ViLBERTForClassification):          # noqa: F811 
                        "v_hidden_dropout_prob": bc.hidden_dropout_prob, "v_attention_probs_dropout_prob": bc.attention_probs_dropout_prob,
                        "v_feature_size": config.get("v_feature_size", 2048), "v_loc_size": 5, "bi_hidden_size": h,
                        "bi_num_attention_heads": bc.num_attention_heads, "num_co_attention_layers": config.get("num_co_layers", 6),
-                       "v_pool": "mean", "classifier_dropout": pc}
+                       "_v_pool": "mean", "_classifier_dropout": pc}
         self._engine = None
         self._anchor = None
         self._ddp_group = None
