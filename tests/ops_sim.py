@@ -14,8 +14,11 @@ ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
 AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD = 0, 1, 2
 
 
+IDENTITY_DROPOUT = False     # smoke mode: let the training-mode code paths run with dropout acting as the identity
+
+
 def _no_dropout(*ps):
-    assert all(p == 0.0 for p in ps), "the simulator covers the dropout-off configuration"
+    assert IDENTITY_DROPOUT or all(p == 0.0 for p in ps), "the simulator covers the dropout-off configuration"
 
 
 def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, scale=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE,
@@ -162,7 +165,9 @@ def i64_to_i32(src, dst, lo, hi, err_flag=None):
 
 
 def dropout(x, y, p, site, seed):
-    raise AssertionError("dropout kernel reached with dropout off")
+    assert IDENTITY_DROPOUT, "dropout kernel reached with dropout off"
+    y.copy_(x)
+    return y
 
 
 def seed_advance(seed):

@@ -123,6 +123,37 @@ def test_more_than_128_regions_and_mixed_input_dtypes(simulated):
     assert (out["logits"].float() - ref_out["logits"]).abs().max().item() <= 2e-2 * ref_out["logits"].abs().max().item()
 
 
+def test_training_mode_code_paths_run(simulated, monkeypatch):
+    """model.train(): every dropout branch of the forward / backward schedule executes (dropout itself acts as the identity in
+    the stand-ins, so the result must still be the oracle's) — for both surfaces that share the engine."""
+    import ops_sim
+    from oracle import vilbert_core_oracle as co
+    from test_vilbert_core_cpu import _model as core_model, _seeded_state
+    monkeypatch.setattr(ops_sim, "IDENTITY_DROPOUT", True)
+    cfg = vo.tiny_config()
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    sd = vo.seeded_state_dict(cfg)
+    batch = vo.synthetic_batch(cfg, batch=2, seq=16, regions=8, seed=41)
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    out = model(**batch)
+    out["loss"].backward()
+    ref_out, ref_grads = vo.loss_and_grads(sd, cfg, batch)
+    assert abs(out["loss"].item() - ref_out["loss"].item()) <= 1e-3
+    _close_grads(model, ref_grads)
+    ccfg = co.tiny_core_config()
+    core = core_model(ccfg)
+    csd = _seeded_state(core)
+    core.load_state_dict(csd, strict=False)
+    core.train()
+    cbatch = co.synthetic_batch(ccfg, batch=2, seq=16, regions=10, seed=42)
+    cout = core(**cbatch)
+    cout["loss"].backward()
+    want, _ = co.loss_and_grads(csd, ccfg, cbatch)
+    assert abs(cout["loss"].item() - want["loss"].item()) <= 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ data parallel (gloo)
 def _dp_worker(rank, world, port, q):
     import os
