@@ -24,6 +24,9 @@ sys.path.insert(0, ROOT)
 METRIC = "ViLBERT train samples/sec"
 UNIT = "samples/s"
 FLOP_PER_SAMPLE_FWD_BWD = 152.07e9   # SURVEY.md §8d (hand-derived, equals torch's FlopCounterMode on the reference)
+# DRAM bytes of one launch of the dominant GEMM shape, from the committed ncu --set full capture
+TRAFFIC_BYTES = 7.94e6
+TRAFFIC_SOURCE = "profiles/r01c_dominant_gemm_full.md (text FFN-1 2048x3072x768: 7.94 MB read = its 7.87 MB of inputs, ~1 KB written; outputs stay in L2)"
 B, T, R = 16, 128, 100
 
 
@@ -125,8 +128,12 @@ def run_reference_arm(args):
     sd = vo.seeded_state_dict(cfg)
     budget = 150.0
     bs = B
+    # the very first pass pays thread-pool start-up and the first touch of 1 GB of weights: warm up BEFORE probing, or a cold
+    # probe halves the batch for no reason (round 1: the N=1 scaling run fell to an 8-sample slice)
+    cpu_port_step(cfg, sd, vo.synthetic_batch(cfg, batch=2, seq=T, regions=R, seed=1))
     while True:
         batch = vo.synthetic_batch(cfg, batch=bs, seq=T, regions=R, seed=1234)
+        cpu_port_step(cfg, sd, batch)
         t0 = time.time()
         cpu_port_step(cfg, sd, batch)
         probe = time.time() - t0
@@ -144,36 +151,147 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "vilbert_base_train_step_bs16_t128_r100", "batch_per_step": bs, "tokens": T, "regions": R},
+            "config": {"workload": "vilbert_base_train_step_bs16_t128_r100", "per_gpu_batch": bs, "tokens": T, "regions": R},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def gemm_kernel_roofline(torch, peaks):
-    """Live, in-process timing of the dominant kernel (gemm_bf16_kernel) on the most FLOP-heavy shape of the step
-    (text FFN: [2048,768]x[768,3072], 18 launches forward and 36 backward-equivalents), CUDA events on the launch stream."""
-    from multimodal_classification_b200 import ops
-    m, n, k = B * T, 3072, 768
-    a = torch.randn(m, k, device="cuda").to(torch.bfloat16)
-    w = torch.randn(n, k, device="cuda").to(torch.bfloat16)
-    bias = torch.randn(n, device="cuda")
-    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
-    pre = torch.empty_like(out)
-    for _ in range(5):
-        ops.gemm(a, w, out, bias=bias, act=ops.ACT_GELU, preact=pre, b_streamed=True)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 50
+def graph_time(torch, fn, rep=20, iters=10):
+    """us per launch of fn(): `rep` back-to-back launches captured in a CUDA graph (as in the graph-replayed step: no ctypes /
+    launch overhead), replayed `iters` times between two CUDA events on the replay stream."""
+    fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(rep):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(iters):
-        ops.gemm(a, w, out, bias=bias, act=ops.ACT_GELU, preact=pre, b_streamed=True)
+        g.replay()
     e.record()
     torch.cuda.synchronize()
-    dt = s.elapsed_time(e) / iters * 1e-3
-    return {"kernel": "gemm_bf16_kernel (cta_group::2 pairs, multicast clusters): text FFN-1 2048x3072x768 +bias+GELU+preact",
-            "tflops": 2.0 * m * n * k / dt / 1e12, "us": dt * 1e6,
-            "frac_of_burst_peak": 2.0 * m * n * k / dt / 1e12 / peaks["bf16_burst"]}
+    return s.elapsed_time(e) / (iters * rep) * 1e3
+
+
+# every GEMM site of the bs-16 step: (name, M, N, K, launches per step in each direction, GELU epilogue) -- SURVEY.md Appendix B
+GEMM_SITES = [("t.qkv", 2048, 2304, 768, 12, 0), ("t.attn_out", 2048, 768, 768, 12, 0), ("t.ffn1", 2048, 3072, 768, 18, 1),
+              ("t.ffn2", 2048, 768, 3072, 18, 0), ("v.qkv", 1600, 3072, 1024, 12, 0), ("v.1024", 1600, 1024, 1024, 18, 0),
+              ("v.ffn1", 1600, 1024, 1024, 12, 1), ("c.tqkv", 2048, 3072, 768, 6, 0), ("c.dense2", 2048, 768, 1024, 6, 0),
+              ("img_emb", 1600, 1024, 2048, 1, 0)]
+
+
+def gemm_family_roofline(torch, peaks, wgrad_ctas):
+    """The dominant kernel FAMILY, honestly: every (site, direction) GEMM of the step is timed live (CUDA events over graph
+    replays, launched with the engine's own epilogue flags), and the family figure is sum(2MNK x launches) / sum(time x
+    launches) -- not the best shape.  Weight gradients are timed twice: chip-wide and with the engine's SM cap (they run on
+    side streams under that cap, in the shadow of the dgrad chain)."""
+    from multimodal_classification_b200 import ops
+    bf = torch.bfloat16
+
+    def rnd(*shape):
+        return (torch.randn(*shape, device="cuda") * 0.5).to(bf)
+    rows, fl_sum, t_sum, t_sum_capped = [], 0.0, 0.0, 0.0
+    for name, m, n, k, cnt, gelu in GEMM_SITES:
+        x, w, bias = rnd(m, k), rnd(n, k), torch.randn(n, device="cuda")
+        y, pre, dy, dx, aux = (torch.empty(m, n, device="cuda", dtype=bf), torch.empty(m, n, device="cuda", dtype=bf), rnd(m, n),
+                               torch.empty(m, k, device="cuda", dtype=bf), rnd(m, k))
+        dw = torch.zeros(n, k, device="cuda")
+        if gelu:
+            t_f = graph_time(torch, lambda: ops.gemm(x, w, y, bias=bias, act=ops.ACT_GELU, preact=pre, b_streamed=True))
+        else:
+            t_f = graph_time(torch, lambda: ops.gemm(x, w, y, bias=bias, b_streamed=True))
+        mode = ops.AUX_MUL_GELU_GRAD if name in ("t.ffn2",) else ops.AUX_ADD     # the dgrad of FFN-2 carries gelu' of FFN-1
+        t_d = graph_time(torch, lambda: ops.gemm(dy, w, dx, b_mn_major=True, aux=aux, aux_mode=mode, b_streamed=True))
+        t_w = graph_time(torch, lambda: ops.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, d_streamed=True))
+        t_wc = graph_time(torch, lambda: ops.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, d_streamed=True, max_ctas=wgrad_ctas))
+        fl = 2.0 * m * n * k
+        for d, t in (("fwd", t_f), ("dgrad", t_d), ("wgrad", t_w)):
+            rows.append({"site": name, "dir": d, "m": m, "n": n, "k": k, "launches_per_step": cnt, "us": t, "tflops": fl / t / 1e6})
+        fl_sum += 3 * cnt * fl
+        t_sum += cnt * (t_f + t_d + t_w)
+        t_sum_capped += cnt * (t_f + t_d + t_wc)
+    best = max(rows, key=lambda r: r["tflops"])
+    worst = min(rows, key=lambda r: r["tflops"])
+    dominant = max(rows, key=lambda r: r["us"] * r["launches_per_step"])
+    return {"family_tflops": fl_sum / t_sum / 1e6, "family_tflops_wgrad_capped": fl_sum / t_sum_capped / 1e6,
+            "serial_us_per_step": t_sum, "serial_us_per_step_wgrad_capped": t_sum_capped, "flop_per_step": fl_sum,
+            "best": best, "worst": worst, "dominant": dominant, "rows": rows}
+
+
+def time_roi_stage(torch, peaks):
+    """BASELINE.json configs[2] (driver-visible): the ResNet-152 C5 + RoI feature stage, images/s at the reference's own shape
+    (600x600, RoIPool 14x14, resnet152_roi.py:126-133) and at the BASELINE shape (448x448, RoIAlign 7x7), batch 1 and 16, plus
+    the RoI pooling kernels alone against the measured HBM peak.  FLOPs per image: 214.9 / 104.1 GF."""
+    from multimodal_classification_b200 import ops
+    from multimodal_classification_b200.resnet152_roi import ResNet152ROIExtractor
+    out = {"legs": []}
+    for size, roi, mode, gf in ((600, 14, "roi_pool", 214.9), (448, 7, "roi_align", 104.1)):
+        torch.manual_seed(0)
+        ext = ResNet152ROIExtractor(device="cuda", weights=None, roi_size=roi, image_size=size, pool_mode=mode)
+        for b in (1, 16):
+            imgs = torch.randn(b, 3, size, size, device="cuda")
+            for _ in range(3):
+                ext.extract_batch(imgs)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            iters = 10
+            s.record()
+            for _ in range(iters):
+                ext.extract_batch(imgs)
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / iters
+            out["legs"].append({"image": size, "pool": f"{mode}-{roi}", "batch": b, "ms": ms, "images_per_s": b / ms * 1e3,
+                                "tflops": gf * b / ms, "frac_of_burst_bf16": gf * b / ms / peaks["bf16_burst"]})
+        del ext
+    # the pooling kernels alone: 36 boxes on one C4 map (stride 16, 1024 channels), bytes = map read once + output written once
+    for size, roi, mode in ((600, 14, "roi_pool"), (448, 7, "roi_align")):
+        hw = (size + 15) // 16
+        x = (torch.randn(1, hw, hw, 1024, device="cuda")).to(torch.bfloat16)
+        g = torch.Generator(device="cpu").manual_seed(0)
+        xy = torch.rand(36, 2, generator=g) * size * 0.5
+        wh = torch.rand(36, 2, generator=g) * size * 0.45 + 32
+        rois = torch.cat([torch.zeros(36, 1), xy, xy + wh], 1).clamp(max=size - 1).cuda().contiguous()
+        o = torch.empty(36, roi, roi, 1024, device="cuda", dtype=torch.bfloat16)
+        if mode == "roi_pool":
+            us = graph_time(torch, lambda: ops.roi_pool_nhwc(x, rois, o, 1.0 / 16))
+        else:
+            us = graph_time(torch, lambda: ops.roi_align_nhwc(x, rois, o, 1.0 / 16, 2, False))
+        nbytes = x.numel() * 2 + o.numel() * 2
+        out.setdefault("kernels", []).append({"kernel": f"{mode}_nhwc_kernel", "image": size, "us": us, "bytes": nbytes,
+                                              "gbs": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / peaks["hbm"]})
+    return out
+
+
+def time_inference_sweep(torch, model, cfg, vo, dev, sizes=(16, 512)):
+    """BASELINE.json configs[4], second half: eval-mode forward throughput (no gradient state kept), resident inputs."""
+    rows = []
+    was_training = model.training
+    model.eval()
+    for bs in sizes:
+        batch = {k: v.to(dev) for k, v in vo.synthetic_batch(cfg, batch=bs, seq=T, regions=R, seed=1234).items() if k != "labels"}
+        with torch.no_grad():
+            for _ in range(3):
+                out = model(**batch)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            iters = 10
+            s.record()
+            for _ in range(iters):
+                out = model(**batch)
+            e.record()
+            torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / iters
+        rows.append({"batch": bs, "ms": ms, "samples_per_s": bs / ms * 1e3, "tflops": 50.83 * bs / ms,
+                     "finite": bool(torch.isfinite(out["logits"]).all())})
+        model._engine.plans.clear()      # the bs-512 plan holds ~28 GB of activations
+        torch.cuda.empty_cache()
+    model.train(was_training)
+    return rows
 
 
 def time_ingest(torch, dev, step, timed, steps, **loader_kw):
@@ -280,12 +398,14 @@ def main():
 
     cfg = get_facebook_vilbert_config()
     torch.manual_seed(0)
+    grad_exchange = "none (1 GPU)"
     model = ViLBERTForClassification(cfg, num_labels=2).to(dev)
     model.train(not args.eval_dropout_off)
     if world > 1 and os.environ.get("VB_DDP_SKIP", "0") != "1":      # VB_DDP_SKIP: diagnostic only (replicas without exchange)
         if os.environ.get("VB_DDP_FLUSH_MB"):
             vb_ddp.FLUSH_BYTES = int(os.environ["VB_DDP_FLUSH_MB"]) << 20
-        vb_ddp.attach(model, dist.group.WORLD, compress=None if os.environ.get("VB_DDP_FP32", "0") == "1" else "bf16")
+        grad_exchange = "fp32" if os.environ.get("VB_DDP_FP32", "0") == "1" else "bf16"
+        vb_ddp.attach(model, dist.group.WORLD, compress=None if grad_exchange == "fp32" else "bf16")
     host = vo.synthetic_batch(cfg, batch=B, seq=T, regions=R, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -361,6 +481,29 @@ def main():
         opt_step()
     ms_opt = timed(opt_step, args.steps)
 
+    # ---- the reference's own loop around the same step (nodes.py:757-760, 784-799): stock AdamW over the 523 parameter
+    #      views, clip_grad_norm_, LambdaLR warm-up schedule, loss read back -- on a second replica (own optimizer state)
+    ms_stock = None
+    if world == 1 and os.environ.get("VB_BENCH_SKIP_STOCK", "0") != "1":
+        from transformers import get_linear_schedule_with_warmup
+        stock = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=0.01, eps=1e-8)
+        sched = get_linear_schedule_with_warmup(stock, 10, 10 ** 6)
+
+        def stock_step():
+            stock.zero_grad()
+            out = model(**resident)
+            loss = out["loss"]
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            stock.step()
+            sched.step()
+            return loss.item()
+        for _ in range(3):
+            stock_step()
+        n_stock = max(5, args.steps // 2)
+        ms_stock = timed(stock_step, n_stock) / n_stock
+        del stock, sched
+
     # ---- the same step fed by the feature-store loader: records decoded from an in-memory LMDB image
     #      by the producer thread, one pinned blob + one H2D + one unpack launch per batch, overlapped with the previous step
     ingest = None
@@ -372,31 +515,59 @@ def main():
 
     if rank == 0:
         step_tflops = FLOP_PER_SAMPLE_FWD_BWD * value / world / 1e12      # per GPU
-        dom = gemm_kernel_roofline(torch, peaks)
-        # dominant kernel (the GEMM family is ~70 % of the step): algorithmic FLOPs of one launch / its CUDA-event time, against
-        # the measured BURST bf16 peak (a kernel timed alone); `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of that
-        # launch from the ncu --set full capture in profiles/r01c_dominant_gemm_full.md (inputs 7.87 MB; the 25 MB of outputs
-        # stay in L2 for the next kernel).  The whole step against the SUSTAINED peak is reported beside it.
-        roofline = {"bound": "tensor", "achieved": dom["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                    "frac": dom["tflops"] / peaks["bf16_burst"], "traffic": 7.94e6, "traffic_unit": "bytes per launch (DRAM)",
-                    "kernel": dom["kernel"], "us_per_launch": dom["us"], "flop_per_launch": 2.0 * 2048 * 3072 * 768,
+        fam = gemm_family_roofline(torch, peaks, eng.wgrad_ctas)
+        # Dominant kernel FAMILY (gemm_bf16_kernel: ~70 % of the step's kernel time): `achieved` is the launch-weighted figure over
+        # all 30 (site, direction) GEMMs of the step, each timed live with CUDA events; best / worst / dominant single shapes
+        # beside it.  Peak = the measured BURST bf16 figure (kernels timed alone; the 0.1 s timed region of the step runs at
+        # full clocks too).  `traffic` = dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant shape from
+        # the ncu --set full capture named in `traffic_source`.
+        roofline = {"bound": "tensor", "achieved": fam["family_tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                    "frac": fam["family_tflops"] / peaks["bf16_burst"],
+                    "kernel": "gemm_bf16_kernel family (tcgen05 cta_group::2 pairs, TMA multicast clusters): 30 (site, direction) shapes of the step, launch-weighted",
+                    "flop_per_step_family": fam["flop_per_step"], "serial_us_per_step": fam["serial_us_per_step"],
+                    "as_scheduled": {"achieved": fam["family_tflops_wgrad_capped"], "frac": fam["family_tflops_wgrad_capped"] / peaks["bf16_burst"],
+                                     "serial_us_per_step": fam["serial_us_per_step_wgrad_capped"],
+                                     "note": f"weight-gradient GEMMs capped to {eng.wgrad_ctas} CTAs as the engine launches them (side streams)"},
+                    "best": {k: fam["best"][k] for k in ("site", "dir", "us", "tflops")},
+                    "worst": {k: fam["worst"][k] for k in ("site", "dir", "us", "tflops")},
+                    "dominant": {k: fam["dominant"][k] for k in ("site", "dir", "us", "tflops", "launches_per_step")},
+                    "traffic": TRAFFIC_BYTES, "traffic_unit": "bytes per launch (DRAM) of the dominant shape", "traffic_source": TRAFFIC_SOURCE,
                     "peak_source": peaks["source"],
-                    "step": {"achieved": step_tflops, "peak": peaks["bf16_sustained"], "frac": step_tflops / peaks["bf16_sustained"],
-                             "unit": "TFLOP/s", "scope": "whole step: %d samples x 152.07 GFLOP per graph replay, sustained bf16 peak" % B}}
+                    "step": {"achieved": step_tflops, "peak": peaks["bf16_burst"], "frac": step_tflops / peaks["bf16_burst"],
+                             "unit": "TFLOP/s", "scope": "whole step: %d samples x 152.07 GFLOP per graph replay, BURST bf16 peak (0.1 s region at full clocks)" % B,
+                             "frac_of_sustained": step_tflops / peaks["bf16_sustained"]},
+                    "per_shape": [{k: (round(r[k], 2) if isinstance(r[k], float) else r[k]) for k in ("site", "dir", "us", "tflops")} for r in fam["rows"]]}
+        roi = inference = None
+        if world == 1 and os.environ.get("VB_BENCH_SKIP_EXTRA", "0") != "1":
+            try:
+                roi = time_roi_stage(torch, peaks)
+            except Exception as e:
+                roi = {"error": repr(e)[:200]}
+            try:
+                inference = time_inference_sweep(torch, model, cfg, vo, dev)
+            except Exception as e:
+                inference = {"error": repr(e)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "vilbert_base_train_step_bs16_t128_r100", "per_gpu_batch": B, "global_batch": B * world,
                            "tokens": T, "regions": R, "dropout": bool(model.training), "step": "fwd+bwd (+bf16 weight-shadow refresh)",
-                           "parallelism": f"dp{world}", "l2": "working set ~2 GB/step (weights+grads) > 126 MB L2, no flush",
+                           "parallelism": f"dp{world}", "grad_exchange": grad_exchange, "l2": "working set ~2 GB/step (weights+grads) > 126 MB L2, no flush",
                            "cuda_graphs": eng.use_graphs},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "with_fused_optimizer": {"value": world * B / (ms_opt / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_opt / args.steps,
                                          "step": "fwd+bwd + fused clip/AdamW/bf16-shadow pass (2 launches)"},
                 "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "roofline": roofline, "clocks": clocks}
+        if ms_stock is not None:
+            line["with_stock_optimizer"] = {"value": B / (ms_stock * 1e-3), "unit": UNIT, "ms_per_step": ms_stock,
+                                            "step": "the reference's loop (nodes.py:784-799): zero_grad, fwd, bwd, clip_grad_norm_, torch.optim.AdamW.step, LambdaLR.step, loss.item()"}
         if ingest is not None:
             line["ingest"] = ingest
+        if roi is not None:
+            line["roi_stage"] = roi
+        if inference is not None:
+            line["inference"] = inference
         if world == 1 and not args.no_cpu_baseline:
             v, cores, n = time_cpu_port(25.0, B)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -69,7 +69,7 @@ typedef struct vb_gemm_args {
   int32_t accumulate;  /* fp32 output only: D += result (gradient accumulation / split-K) */
   int32_t act;         /* vb_act */
   int32_t aux_mode;    /* vb_aux_mode */
-  int32_t block_n;     /* 0 = auto; else a preferred tile width 64 | 96 | 128 | 192 | 256 (ignored when illegal for the layout) */
+  int32_t block_n;     /* 0 = auto; else a preferred tile width, a multiple of 32 in [64, 256] (ignored when illegal for the layout) */
   int32_t splits;      /* 0 = auto (1 unless fp32+accumulate); >1 requires d_is_f32 && accumulate */
   int32_t max_ctas;    /* 0 = all SMs; otherwise cap the persistent grid (stream co-scheduling) */
   int32_t b_streamed;  /* B is read once per step (a weight matrix): load it with the L2 evict-first hint */
@@ -91,7 +91,7 @@ int vb_gemm_debug_occupancy(int smem_bytes, int* blocks_per_sm, int* clusters);
  * them, nothing is stored.  `seed` is a DEVICE pointer so that a captured CUDA graph sees a new seed on
  * every replay.
  * ---------------------------------------------------------------------------------------------- */
-typedef enum vb_dtype { VB_DT_F32 = 0, VB_DT_I32 = 1, VB_DT_I64 = 2 } vb_dtype;
+typedef enum vb_dtype { VB_DT_F32 = 0, VB_DT_I32 = 1, VB_DT_I64 = 2, VB_DT_BF16 = 3 } vb_dtype;
 
 /* y = LayerNorm(dropout_in(x) + res) * gamma + beta, then dropout_out  — BertLayerNorm (eps inside the sqrt, biased
  * variance) fused with the dropout and residual add that precede it:
@@ -170,6 +170,33 @@ int vb_i64_to_i32(const int64_t* src, int32_t* dst, int32_t n, int32_t lo, int32
 int vb_dropout_bf16(const void* x, void* y, int64_t n, float p, uint32_t site, const uint64_t* seed, void* stream);
 /* *seed = lcg(*seed): one tiny launch at the head of every training forward (dropout mask stream) */
 int vb_seed_advance(uint64_t* seed, void* stream);
+/* the same, and the new value is also written to *snapshot: every batch geometry ("plan") keeps the seed its own last
+ * forward drew, so that its backward regenerates the right masks whatever other forwards ran in between */
+int vb_seed_advance_to(uint64_t* seed, uint64_t* snapshot, void* stream);
+
+/* Batch staging in ONE launch: what ViLBERTForClassification.forward (models/vilbert_facebook_arch.py:610-641) receives ->
+ * the static buffers the captured graphs read.  Segment kinds:
+ *   VB_STAGE_INDEX     int64 | int32 -> int32 with the range check [lo, hi) that nn.Embedding / nn.CrossEntropyLoss apply;
+ *                      a violation ORs `err_bit` into *err_flag (the host raises) and stores `lo` (nothing downstream can
+ *                      index out of bounds); with err_bit = VB_STAGE_ERR_LABEL the value -100 (CrossEntropyLoss's
+ *                      ignore_index) is legal and kept
+ *   VB_STAGE_MASK      int64 | int32 | fp32 attention mask -> (1.0f - m) * -10000.0f, bit-exact with :530-540
+ *   VB_STAGE_FEAT      fp32 | bf16 region features -> bf16 (round to nearest even)
+ *   VB_STAGE_COPY_F32  fp32 -> fp32 (the 5-d boxes) */
+#define VB_STAGE_MAX_SEGS 8
+#define VB_IGNORE_INDEX (-100)
+typedef enum vb_stage_kind { VB_STAGE_INDEX = 0, VB_STAGE_MASK = 1, VB_STAGE_FEAT = 2, VB_STAGE_COPY_F32 = 3 } vb_stage_kind;
+typedef enum vb_stage_err { VB_STAGE_ERR_ID = 1, VB_STAGE_ERR_TYPE = 2, VB_STAGE_ERR_LABEL = 4 } vb_stage_err;
+typedef struct vb_stage_seg {
+  const void* src;
+  void* dst;
+  int64_t n;        /* elements; 0 = segment absent */
+  int32_t kind;     /* vb_stage_kind */
+  int32_t dtype;    /* vb_dtype of src */
+  int32_t lo, hi;   /* VB_STAGE_INDEX: legal range [lo, hi) */
+  int32_t err_bit;  /* VB_STAGE_INDEX: vb_stage_err bit */
+} vb_stage_seg;
+int vb_stage_batch(const vb_stage_seg* segs, int32_t nseg, int32_t* err_flag, void* stream);
 /* dx = dy * act'(y) for tanh (BertPooler :407) and ReLU (classifier :575), through the activation output y */
 int vb_act_bwd_bf16(const void* dy, const void* y, void* dx, int64_t n, int32_t act, void* stream);
 /* image_location_embeddings (Linear(5,1024), models/vilbert_facebook_arch.py:92-94,102): forward term and its gradients */
@@ -179,7 +206,9 @@ int vb_loc_embed_bwd(const void* ds, const float* loc, float* dw, float* db, int
                      void* stream);
 /* classifier tail Linear(1024,num_labels) + CrossEntropyLoss(mean), models/vilbert_facebook_arch.py:577, 637-639.
  * fwd: logits fp32 [b,c], probs = softmax(logits), *loss (labels may be NULL -> loss 0).
- * bwd: dlogits = *dloss * (probs - onehot)/b + dlogits_ext;  dw[c,k], db[c] (overwritten), dh bf16 [b,k]. */
+ * bwd: dlogits = *dloss * (probs - onehot)/nv + dlogits_ext;  dw[c,k], db[c] (overwritten), dh bf16 [b,k].
+ * Labels equal to VB_IGNORE_INDEX (-100, the default ignore_index of nn.CrossEntropyLoss) contribute neither loss nor
+ * gradient and nv counts the others (all ignored -> loss NaN, as torch). */
 int vb_cls_ce_fwd(const void* h, const float* w, const float* bias, const int32_t* labels, float* logits, float* probs,
                   float* loss, int32_t bsz, int32_t kdim, int32_t c, void* stream);
 int vb_cls_ce_bwd(const void* h, const float* w, const int32_t* labels, const float* probs, const float* dloss,

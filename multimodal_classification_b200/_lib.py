@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvilbert_b200.so")
+# VB_LIB: an alternative build of the SAME library (e.g. the -DVB_GEMM_TRACE instrumentation build used by tools/gemm_trace.py)
+LIB_PATH = os.environ.get("VB_LIB") or os.path.join(_HERE, "libvilbert_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
 AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD = 0, 1, 2
@@ -78,7 +79,15 @@ class AdamWArgs(C.Structure):
     ]
 
 
-DT_F32, DT_I32, DT_I64 = 0, 1, 2
+class StageSeg(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("n", C.c_int64), ("kind", C.c_int32), ("dtype", C.c_int32),
+                ("lo", C.c_int32), ("hi", C.c_int32), ("err_bit", C.c_int32)]
+
+
+DT_F32, DT_I32, DT_I64, DT_BF16 = 0, 1, 2, 3
+STAGE_INDEX, STAGE_MASK, STAGE_FEAT, STAGE_COPY_F32 = 0, 1, 2, 3
+STAGE_ERR_ID, STAGE_ERR_TYPE, STAGE_ERR_LABEL = 1, 2, 4
+IGNORE_INDEX = -100
 
 _lib = None
 
@@ -116,6 +125,8 @@ def _declare(l: C.CDLL) -> None:
         "vb_i64_to_i32": [vp, vp, i32, i32, i32, vp, vp],
         "vb_dropout_bf16": [vp, vp, i64, f32, u32, vp, vp],
         "vb_seed_advance": [vp, vp],
+        "vb_seed_advance_to": [vp, vp, vp],
+        "vb_stage_batch": [C.POINTER(StageSeg), i32, vp, vp],
         "vb_act_bwd_bf16": [vp, vp, vp, i64, i32, vp],
         "vb_loc_embed_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
         "vb_loc_embed_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],

@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(256) cls_fwd_kernel(const __nv_bfloat16* h, co
   }
   __syncthreads();
   if (warp == 0) {
-    float l = 0.f;
+    float l = 0.f, nv = 0.f;
     for (int bi = lane; bi < bsz; bi += 32) {
       float mx = -INFINITY;
       for (int ci = 0; ci < c; ++ci) mx = fmaxf(mx, s_logits[bi * c + ci]);
@@ -594,10 +594,12 @@ __global__ void __launch_bounds__(256) cls_fwd_kernel(const __nv_bfloat16* h, co
       for (int ci = 0; ci < c; ++ci) se += expf(s_logits[bi * c + ci] - mx);
       const float lse = mx + logf(se);
       for (int ci = 0; ci < c; ++ci) probs[bi * c + ci] = expf(s_logits[bi * c + ci] - lse);
-      if (labels) l += lse - s_logits[bi * c + labels[bi]];
+      // nn.CrossEntropyLoss() defaults: ignore_index = -100, mean over the samples that are NOT ignored
+      if (labels && labels[bi] != VB_IGNORE_INDEX) { l += lse - s_logits[bi * c + labels[bi]]; nv += 1.f; }
     }
     l = warp_sum(l);
-    if (lane == 0 && loss) *loss = labels ? l / (float)bsz : 0.f;
+    nv = warp_sum(nv);
+    if (lane == 0 && loss) *loss = labels ? l / nv : 0.f;     // every label ignored -> 0/0 = NaN, as torch
   }
 }
 
@@ -606,11 +608,21 @@ __global__ void __launch_bounds__(256) cls_bwd_kernel(const __nv_bfloat16* h, co
                                                       const float* probs, const float* dloss, const float* dlogits_ext,
                                                       float* dw, float* db, __nv_bfloat16* dh, int bsz, int kdim, int c) {
   __shared__ float s_dl[8192];
+  __shared__ int s_nv;
   const float gl = (dloss && labels) ? *dloss : 0.f;
+  if (threadIdx.x == 0) s_nv = 0;
+  __syncthreads();
+  if (labels) {
+    int mine = 0;
+    for (int bi = threadIdx.x; bi < bsz; bi += blockDim.x) mine += labels[bi] != VB_IGNORE_INDEX ? 1 : 0;
+    if (mine) atomicAdd(&s_nv, mine);
+  }
+  __syncthreads();
+  const float inv_nv = 1.f / (float)s_nv;
   for (int o = threadIdx.x; o < bsz * c; o += blockDim.x) {
     const int bi = o / c, ci = o % c;
     float g = 0.f;
-    if (labels) g = gl * (probs[o] - (labels[bi] == ci ? 1.f : 0.f)) / (float)bsz;
+    if (labels && labels[bi] != VB_IGNORE_INDEX) g = gl * (probs[o] - (labels[bi] == ci ? 1.f : 0.f)) * inv_nv;
     if (dlogits_ext) g += dlogits_ext[o];
     s_dl[o] = g;
   }
@@ -632,6 +644,70 @@ __global__ void __launch_bounds__(256) cls_bwd_kernel(const __nv_bfloat16* h, co
     for (int bi = 0; bi < bsz; ++bi) acc += s_dl[bi * c + threadIdx.x];
     db[threadIdx.x] = acc;
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ batch staging
+// ONE launch moves a whole batch from the caller's tensors into the plan's static buffers (the graphs read those addresses):
+// ids / token types / labels (int64 or int32 -> int32, range-checked like nn.Embedding / CrossEntropyLoss check them), the
+// two attention masks (-> additive bias, bit-exact (1 - m) * -10000), region features (fp32 -> bf16, or a bf16 copy) and
+// the 5-d boxes (fp32 copy).  Blocks are dealt to the segments in order; a segment with n = 0 takes none.
+struct StageSeg { const void* src; void* dst; long long n; int kind; int dtype; int lo, hi; int err_bit; int first_block; };
+struct StageParams { StageSeg seg[VB_STAGE_MAX_SEGS]; int nseg; int* err_flag; };
+constexpr int STAGE_PER_BLOCK = 256 * 8;
+
+__global__ void __launch_bounds__(256) stage_batch_kernel(const StageParams p) {
+  int si = 0;
+#pragma unroll 1
+  for (int i = 1; i < p.nseg; ++i) if ((int)blockIdx.x >= p.seg[i].first_block) si = i;
+  const StageSeg& g = p.seg[si];
+  const long long base = (long long)((int)blockIdx.x - g.first_block) * STAGE_PER_BLOCK;
+  if (g.kind == VB_STAGE_FEAT && base + STAGE_PER_BLOCK <= g.n && (g.n & 7) == 0) {
+    // vector path: 8 elements per thread
+    const long long i = base + threadIdx.x * 8;
+    if (g.dtype == VB_DT_F32) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(g.src) + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(g.src) + i) + 1);
+      uint4 o;
+      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.dst) + i) = o;
+    } else {
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.dst) + i) =
+          __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(g.src) + i));
+    }
+    return;
+  }
+  bool bad = false;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const long long i = base + j * 256 + threadIdx.x;
+    if (i >= g.n) break;
+    if (g.kind == VB_STAGE_INDEX) {
+      const long long v = g.dtype == VB_DT_I64 ? static_cast<const long long*>(g.src)[i] : (long long)static_cast<const int*>(g.src)[i];
+      const bool ignored = g.err_bit == VB_STAGE_ERR_LABEL && v == VB_IGNORE_INDEX;   // CrossEntropyLoss(ignore_index=-100)
+      const bool ok = (v >= g.lo && v < g.hi) || ignored;
+      bad |= !ok;
+      static_cast<int*>(g.dst)[i] = ok ? (int)v : g.lo;     // clamped: nothing downstream may index out of bounds
+    } else if (g.kind == VB_STAGE_MASK) {
+      float m;
+      if (g.dtype == VB_DT_I64) m = static_cast<float>(static_cast<const long long*>(g.src)[i]);
+      else if (g.dtype == VB_DT_I32) m = static_cast<float>(static_cast<const int*>(g.src)[i]);
+      else m = static_cast<const float*>(g.src)[i];
+      static_cast<float*>(g.dst)[i] = (1.0f - m) * -10000.0f;
+    } else if (g.kind == VB_STAGE_FEAT) {
+      static_cast<__nv_bfloat16*>(g.dst)[i] = g.dtype == VB_DT_F32 ? __float2bfloat16_rn(static_cast<const float*>(g.src)[i])
+                                                                   : static_cast<const __nv_bfloat16*>(g.src)[i];
+    } else {
+      static_cast<float*>(g.dst)[i] = static_cast<const float*>(g.src)[i];
+    }
+  }
+  if (bad && p.err_flag) atomicOr(p.err_flag, g.err_bit);
+}
+
+__global__ void seed_advance_to_kernel(unsigned long long* seed, unsigned long long* snapshot) {
+  const unsigned long long s = *seed * 6364136223846793005ull + 1442695040888963407ull;
+  *seed = s;
+  *snapshot = s;
 }
 
 }  // namespace vb
@@ -870,6 +946,36 @@ extern "C" int vb_cls_ce_bwd(const void* h, const float* w, const int32_t* label
 __global__ void seed_advance_kernel(unsigned long long* seed) {
   *seed = *seed * 6364136223846793005ull + 1442695040888963407ull;
 }
+extern "C" int vb_stage_batch(const vb_stage_seg* segs, int32_t nseg, int32_t* err_flag, void* stream) {
+  VB_REQUIRE(segs != nullptr && nseg > 0 && nseg <= VB_STAGE_MAX_SEGS, "1..VB_STAGE_MAX_SEGS segments");
+  StageParams p;
+  p.nseg = nseg;
+  p.err_flag = err_flag;
+  int blocks = 0;
+  for (int i = 0; i < nseg; ++i) {
+    const vb_stage_seg& g = segs[i];
+    VB_REQUIRE(g.n >= 0 && (g.n == 0 || (g.src && g.dst)), "segment pointers");
+    VB_REQUIRE(g.kind >= VB_STAGE_INDEX && g.kind <= VB_STAGE_COPY_F32, "segment kind");
+    VB_REQUIRE(g.kind != VB_STAGE_INDEX || g.dtype == VB_DT_I64 || g.dtype == VB_DT_I32, "index segments are int64 or int32");
+    VB_REQUIRE(g.kind != VB_STAGE_FEAT || g.dtype == VB_DT_F32 || g.dtype == VB_DT_BF16, "feature segments are fp32 or bf16");
+    VB_REQUIRE(g.kind != VB_STAGE_FEAT || (aligned16(g.src) && aligned16(g.dst)), "feature segments must be 16-byte aligned");
+    p.seg[i].src = g.src; p.seg[i].dst = g.dst; p.seg[i].n = g.n; p.seg[i].kind = g.kind; p.seg[i].dtype = g.dtype;
+    p.seg[i].lo = g.lo; p.seg[i].hi = g.hi; p.seg[i].err_bit = g.err_bit; p.seg[i].first_block = blocks;
+    blocks += static_cast<int>((g.n + STAGE_PER_BLOCK - 1) / STAGE_PER_BLOCK);
+  }
+  VB_REQUIRE(blocks > 0, "nothing to stage");
+  stage_batch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
+extern "C" int vb_seed_advance_to(uint64_t* seed, uint64_t* snapshot, void* stream) {
+  VB_REQUIRE(seed != nullptr && snapshot != nullptr, "null seed");
+  seed_advance_to_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)seed, (unsigned long long*)snapshot);
+  VB_CUDA_CHECK(cudaGetLastError());
+  return VB_OK;
+}
+
 extern "C" int vb_seed_advance(uint64_t* seed, void* stream) {
   VB_REQUIRE(seed != nullptr, "null seed");
   seed_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)seed);

@@ -239,9 +239,39 @@ def dropout(x, y, p, site, seed):
     return y
 
 
-def seed_advance(seed):
-    _need_cuda(seed)
-    _lib.check(_lib.lib().vb_seed_advance(seed.data_ptr(), _stream()), "vb_seed_advance")
+def seed_advance(seed, snapshot=None):
+    """Advance the engine's dropout seed; with `snapshot`, also record the new value in a plan-owned buffer."""
+    _need_cuda(seed, snapshot)
+    if snapshot is None:
+        _lib.check(_lib.lib().vb_seed_advance(seed.data_ptr(), _stream()), "vb_seed_advance")
+    else:
+        _lib.check(_lib.lib().vb_seed_advance_to(seed.data_ptr(), snapshot.data_ptr(), _stream()), "vb_seed_advance_to")
+
+
+_STAGE_DT = {torch.float32: _lib.DT_F32, torch.int32: _lib.DT_I32, torch.int64: _lib.DT_I64, torch.bfloat16: _lib.DT_BF16}
+
+
+def stage_batch(segs, err_flag=None):
+    """One launch for the whole batch hand-over (vb_stage_batch).  `segs`: [(kind, src, dst, lo, hi, err_bit)]; sources must be
+    contiguous CUDA tensors of a dtype their kind accepts."""
+    arr = (_lib.StageSeg * len(segs))()
+    for i, (kind, src, dst, lo, hi, bit) in enumerate(segs):
+        _need_cuda(src, dst)
+        if src.dtype not in _STAGE_DT:
+            raise _lib.VbError(f"input dtype {src.dtype} is not supported by the staging kernel")
+        if kind == _lib.STAGE_INDEX and src.dtype not in (torch.int64, torch.int32):
+            raise _lib.VbError(f"ids / token types / labels must be int64 or int32, got {src.dtype}")
+        if kind == _lib.STAGE_MASK and src.dtype == torch.bfloat16:
+            raise _lib.VbError("attention mask dtype torch.bfloat16 is not supported (int64, int32, float32)")
+        if kind in (_lib.STAGE_FEAT,) and src.dtype not in (torch.float32, torch.bfloat16):
+            raise _lib.VbError(f"region features must be float32 or bfloat16, got {src.dtype}")
+        if kind == _lib.STAGE_COPY_F32 and src.dtype != torch.float32:
+            raise _lib.VbError(f"spatial locations must be float32, got {src.dtype}")
+        assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel(), (kind, src.shape, dst.shape)
+        a = arr[i]
+        a.src, a.dst, a.n, a.kind, a.dtype = src.data_ptr(), dst.data_ptr(), src.numel(), kind, _STAGE_DT[src.dtype]
+        a.lo, a.hi, a.err_bit = lo, hi, bit
+    _lib.check(_lib.lib().vb_stage_batch(arr, len(segs), _ptr(err_flag), _stream()), "vb_stage_batch")
 
 
 def act_bwd(dy, y, dx, act):

@@ -25,10 +25,45 @@ class FusedAdamW(torch.optim.Optimizer):
                  weight_decay: float = 1e-2, max_grad_norm: Optional[float] = None):
         self.model = model
         self.max_grad_norm = max_grad_norm
-        super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._flat = None
         self._step = 0
+        self._pending_state = None          # moments loaded before the model's flat buffers exist
         self.last_grad_norm: Optional[torch.Tensor] = None
+        super().__init__(list(model.parameters()), dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+    def add_param_group(self, param_group):
+        """One group only: the update is two launches over the model's flat buffers with one set of hyper-parameters.  A second
+        group (per-group lr / weight decay) would be silently ignored by that kernel, so it is refused."""
+        if len(self.param_groups) >= 1:
+            raise VbError("FusedAdamW applies ONE set of hyper-parameters to the model's flat parameter buffer; per-group lr / "
+                          "weight_decay is not supported (use torch.optim.AdamW for that)")
+        super().add_param_group(param_group)
+
+    # the moments are two flat fp32 buffers, not per-parameter entries of self.state: carry them (and the step count, which
+    # drives the bias correction) through state_dict() / load_state_dict() explicitly
+    def state_dict(self):
+        sd = super().state_dict()
+        fused = {"step": self._step}
+        if self._flat is not None:
+            fused["exp_avg"], fused["exp_avg_sq"] = self.exp_avg.clone(), self.exp_avg_sq.clone()
+        elif self._pending_state is not None:
+            fused.update({k: v for k, v in self._pending_state.items() if k != "step"})
+        sd["fused_adamw"] = fused
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        fused = state_dict.pop("fused_adamw", None)
+        super().load_state_dict(state_dict)
+        if fused is None:
+            raise VbError("not a FusedAdamW state_dict (no 'fused_adamw' entry): moments and step count would be lost")
+        self._step = int(fused["step"])
+        if "exp_avg" in fused:
+            if self._flat is not None:
+                self.exp_avg.copy_(fused["exp_avg"])
+                self.exp_avg_sq.copy_(fused["exp_avg_sq"])
+            else:
+                self._pending_state = {"exp_avg": fused["exp_avg"], "exp_avg_sq": fused["exp_avg_sq"]}
 
     def _bind(self):
         eng = self.model._engine
@@ -42,6 +77,12 @@ class FusedAdamW(torch.optim.Optimizer):
             self.exp_avg = torch.zeros(flat.s_end, dtype=torch.float32, device=flat.device)
             self.exp_avg_sq = torch.zeros(flat.s_end, dtype=torch.float32, device=flat.device)
             self._sumsq = torch.zeros(1, dtype=torch.float64, device=flat.device)
+            if self._pending_state is not None:
+                if self._pending_state["exp_avg"].numel() != flat.s_end:
+                    raise VbError("loaded FusedAdamW moments do not match this model's flat parameter layout")
+                self.exp_avg.copy_(self._pending_state["exp_avg"])
+                self.exp_avg_sq.copy_(self._pending_state["exp_avg_sq"])
+                self._pending_state = None
         return flat
 
     def _ranges(self, flat) -> List[Tuple[int, int]]:
@@ -87,9 +128,9 @@ class FusedAdamW(torch.optim.Optimizer):
             a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = g["lr"], g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"]
             a.step = self._step
             _lib.check(lib.vb_adamw_step(C.byref(a), stream), "vb_adamw_step")
-        # the master buffer changed under the parameters' feet (raw pointers): shadows are already current, so tell the
-        # engine not to recast them on the next forward
-        flat._version = flat.versions()
+        # The kernel writes the master buffer through raw pointers, so no parameter's _version moves and the engine does not
+        # recast the (already refreshed) shadows on the next forward.  flat._version is deliberately left alone: an in-place
+        # edit made since the last forward (load_state_dict, a manual change of a frozen tensor) must still trigger a recast.
         return loss
 
     def grad_norm(self) -> float:

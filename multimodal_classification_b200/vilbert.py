@@ -320,6 +320,9 @@ class _Plan:
         self.probs = self.buf("out.probs", (B, self.C), f32)
         self.loss = self.buf("out.loss", (1,), f32)
         self.dloss = self.buf("in.dloss", (1,), f32)
+        # the dropout seed THIS plan's last forward drew: its backward regenerates the masks from it, whatever other
+        # geometries ran forward in between (the engine-wide seed has moved on by then)
+        self.seed = self.buf("in.seed", (1,), torch.int64)
         self.dlogits = self.buf("in.dlogits", (B, self.C), f32)
         # constant one-hot GEMM operands of the vilbert_core surface: region index (position table) and sample index (mean pool)
         self.onehot_r = self.onehot_b = self.inv_r = None
@@ -345,6 +348,19 @@ class _Plan:
         return t
 
 
+class _MappedFlag:
+    """Device-side address of a pinned host tensor (cudaHostGetDevicePointer; with unified addressing it is the host
+    address itself).  Quacks like a tensor for ops._ptr / ops._need_cuda."""
+    is_cuda = True
+
+    def __init__(self, host: torch.Tensor):
+        self._host = host
+        self._ptr = host.data_ptr()
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+
 class _Engine:
     def __init__(self, model: "ViLBERTForClassification", device):
         self.model = model
@@ -362,6 +378,13 @@ class _Engine:
         self.wgrad_ctas = int(os.environ.get("VB_WGRAD_CTAS", "48"))     # measured: 0 -> 5.92 ms, 32 -> 5.86, 48 -> 5.83, 64 -> 5.89 per step
         self._pl = None
         self.launches = 0
+        # range-check verdict of the staging kernel: one int32 in mapped pinned host memory (see _raise_on_bad_indices)
+        self.err_host = torch.zeros(1, dtype=torch.int32)
+        if torch.device(device).type == "cuda":
+            self.err_host = self.err_host.pin_memory()
+        self.err_flag = _MappedFlag(self.err_host)
+        self.strict_inputs = os.environ.get("VB_STRICT_INPUTS", "0") == "1"
+        self.grads_clean = False     # set by ViLBERTForClassification.zero_grad(set_to_none=False)
         self.comm_group = getattr(model, "_ddp_group", None)   # data-parallel: see ddp.attach()
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if self.comm_group is not None else None   # as urgent as the chain: NCCL CTAs must get SM slots while GEMMs are running
         self.comm_compress = getattr(model, "_ddp_compress", None) if self.comm_group is not None else None
@@ -448,7 +471,7 @@ class _Engine:
         res32 = pl.twins.get(res.data_ptr()) if (res is not None and self.fp32_residual) else None
         ops.layernorm_fwd(x, res, f.m(lnkey + ".weight"), f.m(lnkey + ".bias"), y, mean, rstd,
                           p_in=p_in if drop else 0.0, site_in=site, p_out=p_out if drop else 0.0, site_out=site + 1,
-                          seed=self.seed if drop else None, res32=res32, y32=y32)
+                          seed=pl.seed if drop else None, res32=res32, y32=y32)
         if y32 is not None:
             pl.twins[y.data_ptr()] = y32
         return (mean, rstd, site)
@@ -462,7 +485,7 @@ class _Engine:
                           dgamma=f.g(lnkey + ".weight"), dbeta=f.g(lnkey + ".bias"),
                           dbias=f.g(bias_key) if bias_key else None,
                           p_in=p_in if drop else 0.0, site_in=site, p_out=p_out if drop else 0.0, site_out=site + 1,
-                          seed=self.seed if drop else None, res32=res32)
+                          seed=pl.seed if drop else None, res32=res32)
 
     def _bucket_ready(self, name, producers, flush=False):
         """Data-parallel: a gradient bucket has been written by `producers`.  Finished buckets are queued and exchanged in
@@ -500,7 +523,7 @@ class _Engine:
         sv["attn_site"] = self._next_site()
         ops.attention_fwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], ctx, lse, batch=pl.B, heads=heads, sq=S, sk=S,
                           d=H // heads, mask_bias=bias, p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"],
-                          seed=self.seed if pl.dropout else None)
+                          seed=pl.seed if pl.dropout else None)
         ao = pl.buf(tag + ".ao", (M, H))
         self._linear(ctx, p + ".attention.output.dense.weight", ao)
         a = pl.buf(tag + ".a", (M, H))
@@ -540,7 +563,7 @@ class _Engine:
         qkv = sv["qkv"]
         ops.attention_bwd(g_ctx, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["lse"], g_qkv[:, :H], g_qkv[:, H:2 * H],
                           g_qkv[:, 2 * H:], batch=pl.B, heads=heads, sq=S, sk=S, d=H // heads, mask_bias=bias,
-                          p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"], seed=self.seed if pl.dropout else None,
+                          p_drop=p_attn if pl.dropout else 0.0, site=sv["attn_site"], seed=pl.seed if pl.dropout else None,
                           out=sv["ctx"])
         self._linear_bwd(g_qkv, sv["x"], p + ".attention.self.query.weight", rows=3 * H, dx=dx_out,
                          aux=g_xres if g_xres is not None else g_ao, aux_mode=ops.AUX_ADD)
@@ -563,7 +586,7 @@ class _Engine:
         pl.ring.clear()
         pl.twins.clear()
         if pl.dropout:
-            ops.seed_advance(self.seed)
+            ops.seed_advance(self.seed, pl.seed)
         s_v.wait_stream(s_t)
 
         # text embeddings (transformers BertEmbeddings) | visual embeddings (reference :100-104)
@@ -575,7 +598,7 @@ class _Engine:
                            f.m(e + ".position_embeddings.weight").view(-1, H),
                            f.m(e + ".token_type_embeddings.weight").view(-1, H), f.m(e + ".LayerNorm.weight"),
                            f.m(e + ".LayerNorm.bias"), t, mean, rstd, B, T, p_out=ph if pl.dropout else 0.0,
-                           site_out=sv["emb_site"], seed=self.seed if pl.dropout else None,
+                           site_out=sv["emb_site"], seed=pl.seed if pl.dropout else None,
                            y32=pl.buf("emb.t32", (Mt, H), torch.float32) if self.fp32_residual else None)
         if self.fp32_residual:
             pl.twins[t.data_ptr()] = pl.bufs["emb.t32"]      # consumed by the first text LayerNorm only
@@ -622,12 +645,12 @@ class _Engine:
         pc = cfg.get("_classifier_dropout", 0.1)
         pooled_d = pooled
         if pl.dropout:
-            pooled_d = ops.dropout(pooled, pl.buf("head.pooled_d", (B, bi + Hv)), pc, sv["head_site"], self.seed)
+            pooled_d = ops.dropout(pooled, pl.buf("head.pooled_d", (B, bi + Hv)), pc, sv["head_site"], pl.seed)
         hid = pl.buf("head.hid", (B, bi))
         ops.gemm(pooled_d, f.w("classifier.1.weight"), hid, bias=f.m("classifier.1.bias"), act=ops.ACT_RELU)
         hid_d = hid
         if pl.dropout:
-            hid_d = ops.dropout(hid, pl.buf("head.hid_d", (B, bi)), pc, sv["head_site"] + 1, self.seed)
+            hid_d = ops.dropout(hid, pl.buf("head.hid_d", (B, bi)), pc, sv["head_site"] + 1, pl.seed)
         ops.cls_ce_fwd(hid_d, f.m("classifier.4.weight").view(pl.C, bi), f.m("classifier.4.bias"), pl.labels, pl.logits,
                        pl.probs, pl.loss)
         sv.update(t_final=t, v_final=v, v_pool_in=v_in, pooled=pooled, pooled_d=pooled_d, hid=hid, hid_d=hid_d)
@@ -657,7 +680,7 @@ class _Engine:
         t_lse = pl.buf(tag + ".t_lse", (len(ops.attn_blocks(T)) * B, heads, 128), torch.float32)
         ops.attention_fwd(tqkv[:, :bi], vqkv[:, bi:2 * bi], vqkv[:, 2 * bi:], t_ctx, t_lse, batch=B, heads=heads, sq=T,
                           sk=R, d=d, mask_bias=pl.v_bias, p_drop=pa if drop else 0.0, site=sv["site_t"],
-                          seed=self.seed if drop else None)
+                          seed=pl.seed if drop else None)
         t_bo = pl.buf(tag + ".t_bo", (Mt, H))
         self._linear(t_ctx, p + ".biOutput.dense2.weight", t_bo)
         t_att = pl.buf(tag + ".t_att", (Mt, H))
@@ -674,7 +697,7 @@ class _Engine:
             v_lse = pl.buf(tag + ".v_lse", (len(ops.attn_blocks(R)) * B, heads, 128), torch.float32)
             ops.attention_fwd(vqkv[:, :bi], tqkv[:, bi:2 * bi], tqkv[:, 2 * bi:], v_ctx, v_lse, batch=B, heads=heads, sq=R,
                               sk=T, d=d, mask_bias=pl.t_bias, p_drop=pa if drop else 0.0, site=sv["site_v"],
-                              seed=self.seed if drop else None)
+                              seed=pl.seed if drop else None)
             v_bo = pl.buf(tag + ".v_bo", (Mv, Hv))
             self._linear(v_ctx, p + ".biOutput.dense1.weight", v_bo)
             v_att = pl.buf(tag + ".v_att", (Mv, Hv))
@@ -729,13 +752,13 @@ class _Engine:
                        f.g("classifier.4.weight"), f.g("classifier.4.bias"), g_hid_d)
         g_hid = g_hid_d
         if pl.dropout:
-            g_hid = ops.dropout(g_hid_d, pl.buf("g.hid", (B, bi)), cfg.get("_classifier_dropout", 0.1), sv["head_site"] + 1, self.seed)
+            g_hid = ops.dropout(g_hid_d, pl.buf("g.hid", (B, bi)), cfg.get("_classifier_dropout", 0.1), sv["head_site"] + 1, pl.seed)
         g_hid_pre = ops.act_bwd(g_hid, sv["hid"], pl.buf("g.hid_pre", (B, bi)), ops.ACT_RELU)
         g_pooled_d = pl.buf("g.pooled_d", (B, bi + Hv))
         self._linear_bwd(g_hid_pre, sv["pooled_d"], "classifier.1.weight", dx=g_pooled_d)
         g_pooled = g_pooled_d
         if pl.dropout:
-            g_pooled = ops.dropout(g_pooled_d, pl.buf("g.pooled", (B, bi + Hv)), cfg.get("_classifier_dropout", 0.1), sv["head_site"], self.seed)
+            g_pooled = ops.dropout(g_pooled_d, pl.buf("g.pooled", (B, bi + Hv)), cfg.get("_classifier_dropout", 0.1), sv["head_site"], pl.seed)
         g_pool_pre = ops.act_bwd(g_pooled, sv["pooled"], pl.buf("g.pool_pre", (B, bi + Hv)), ops.ACT_TANH)
         s_v.wait_stream(s_t)
         self._linear_bwd(g_pool_pre[:, :bi], sv["t_final"].view(B, T * H)[:, :H], "bert.t_pooler.dense.weight",
@@ -790,7 +813,7 @@ class _Engine:
                            dword=f.g(e + ".word_embeddings.weight"), dpos=f.g(e + ".position_embeddings.weight"),
                            dtype=f.g(e + ".token_type_embeddings.weight"), dgamma=f.g(e + ".LayerNorm.weight"),
                            dbeta=f.g(e + ".LayerNorm.bias"), p_out=ph if pl.dropout else 0.0, site_out=sv["emb_site"],
-                           seed=self.seed if pl.dropout else None)
+                           seed=pl.seed if pl.dropout else None)
         s_t.wait_stream(s_v)
         for side in sides_t + sides_v:
             s_t.wait_stream(side)
@@ -812,7 +835,7 @@ class _Engine:
         B, T, R, Mt, Mv = pl.B, pl.T, pl.R, pl.Mt, pl.Mv
         p = f"bert.encoder.c_layer.{c}"
         drop = pl.dropout
-        seed = self.seed if drop else None
+        seed = pl.seed if drop else None
         sct, scv = f"gct{c & 1}", f"gcv{c & 1}"              # scratch double-buffered by layer parity
         self._scratch_begin(pl, sct)                         # both chains write both qkv-gradient buffers
         self._scratch_begin(pl, scv)
@@ -917,10 +940,12 @@ class _Step(torch.autograd.Function):
             plan.dloss.zero_()
         else:
             plan.dloss.copy_(g_loss.reshape(1))
+        module._raise_on_bad_indices(eng)
         carry = None
         params = module._grad_bindings()                     # [(key, parameter, view into the flat gradient buffer)], cached
-        if any(p.grad is not None for _, p, _ in params):
+        if not eng.grads_clean and any(p.grad is not None for _, p, _ in params):
             carry = {k: p.grad.clone() for k, p, _ in params if p.grad is not None}   # gradient accumulation (rare path)
+        eng.grads_clean = False
         eng._execute(plan, "bwd")
         for k, p, g in params:
             if carry is not None and k in carry:
@@ -986,6 +1011,33 @@ class ViLBERTForClassification(nn.Module):
             eng._grad_cache = cache
         return cache[1]
 
+    def _raise_on_bad_indices(self, eng) -> None:
+        """The staging kernel range-checks ids / token types / labels the way nn.Embedding and nn.CrossEntropyLoss do and
+        ORs a bit into a flag that lives in mapped pinned host memory: reading it costs nothing and needs no stream
+        synchronisation, so the verdict on batch k is raised at the latest when batch k+1 arrives or batch k's backward
+        starts (VB_STRICT_INPUTS=1: synchronise and raise inside the same forward).  Offending values were clamped, so no
+        kernel indexed out of bounds in the meantime."""
+        bits = int(eng.err_host[0])
+        if bits:
+            eng.err_host[0] = 0
+            what = [n for b, n in ((_lib.STAGE_ERR_ID, f"input_ids outside [0, {self.config['vocab_size']})"),
+                                   (_lib.STAGE_ERR_TYPE, "token_type_ids outside [0, 2)"),
+                                   (_lib.STAGE_ERR_LABEL, f"labels outside [0, {self.num_labels}) and != -100")) if bits & b]
+            raise VbError("index out of range in the staged batch: " + "; ".join(what))
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """nn.Module.zero_grad; with set_to_none=False the gradients that are views of the engine's flat buffer are cleared with
+        one fill, and the next backward knows it has nothing to carry over (no per-parameter clone + add)."""
+        eng = self._engine
+        if set_to_none or eng is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        own = {g.data_ptr() for _, _, g in self._grad_bindings()}
+        foreign = [p for p in self.parameters() if p.grad is not None and p.grad.data_ptr() not in own]
+        eng.flat.grad.zero_()
+        for p in foreign:
+            p.grad.zero_()
+        eng.grads_clean = not foreign
+
     def _ensure_engine(self, device) -> _Engine:
         eng = self._engine
         if eng is not None and (not eng.flat.intact() or eng.flat.device != device):
@@ -1021,6 +1073,9 @@ class ViLBERTForClassification(nn.Module):
             eng = self._ensure_engine(device)
             B, T = input_ids.shape
             R = visual_features.shape[1]
+            if T > cfg["max_position_embeddings"]:
+                raise VbError(f"{T} tokens exceed max_position_embeddings = {cfg['max_position_embeddings']} "
+                              "(the position table has no such row)")
             if T > ops.ATTN_MAX_SEQ or R > ops.ATTN_MAX_SEQ:
                 raise VbError(f"sequence lengths above {ops.ATTN_MAX_SEQ} are not supported by the blocked attention (T={T}, R={R})")
             if visual_features.shape[2] != cfg["v_feature_size"] or spatial_locations.shape[-1] != cfg["v_loc_size"]:
@@ -1032,25 +1087,24 @@ class ViLBERTForClassification(nn.Module):
             pl = eng.plans.get(key)
             if pl is None:
                 pl = eng.plans[key] = _Plan(eng, key)
-            # stage the batch into the plan's static buffers (the graphs read these addresses)
-            ops.i64_to_i32(input_ids.contiguous(), pl.ids, 0, cfg["vocab_size"]) if input_ids.dtype == torch.int64 \
-                else pl.ids.copy_(input_ids.reshape(-1))
+            # stage the batch into the plan's static buffers (the graphs read these addresses): ONE launch
+            self._raise_on_bad_indices(eng)          # verdict of the PREVIOUS batch's range checks (no sync on this one)
+            L = _lib
+            segs = [(L.STAGE_INDEX, input_ids.reshape(-1), pl.ids, 0, cfg["vocab_size"], L.STAGE_ERR_ID)]
             if token_type_ids is not None:
-                ops.i64_to_i32(token_type_ids.contiguous(), pl.types, 0, 2) if token_type_ids.dtype == torch.int64 \
-                    else pl.types.copy_(token_type_ids.reshape(-1))
+                segs.append((L.STAGE_INDEX, token_type_ids.reshape(-1), pl.types, 0, 2, L.STAGE_ERR_TYPE))
             if labels is not None:
-                ops.i64_to_i32(labels.contiguous(), pl.labels, 0, self.num_labels) if labels.dtype == torch.int64 \
-                    else pl.labels.copy_(labels.reshape(-1))
+                segs.append((L.STAGE_INDEX, labels.reshape(-1), pl.labels, 0, self.num_labels, L.STAGE_ERR_LABEL))
             if attention_mask is not None:
-                ops.mask_bias(attention_mask.contiguous(), pl.t_bias)
+                segs.append((L.STAGE_MASK, attention_mask.reshape(-1), pl.t_bias.view(-1), 0, 0, 0))
             if visual_attention_mask is not None:
-                ops.mask_bias(visual_attention_mask.contiguous(), pl.v_bias)
-            vf = visual_features.reshape(pl.Mv, -1)
-            if vf.dtype == torch.float32:
-                ops.cast_bf16(vf.contiguous(), pl.feat)
-            else:
-                pl.feat.copy_(vf)
-            pl.loc.copy_(spatial_locations.reshape(pl.Mv, -1))
+                segs.append((L.STAGE_MASK, visual_attention_mask.reshape(-1), pl.v_bias.view(-1), 0, 0, 0))
+            segs.append((L.STAGE_FEAT, visual_features.reshape(-1), pl.feat.view(-1), 0, 0, 0))
+            segs.append((L.STAGE_COPY_F32, spatial_locations.reshape(-1), pl.loc.view(-1), 0, 0, 0))
+            ops.stage_batch([(k, src.contiguous(), dst, lo, hi, bit) for k, src, dst, lo, hi, bit in segs], eng.err_flag)
+            if eng.strict_inputs:
+                torch.cuda.current_stream().synchronize()
+                self._raise_on_bad_indices(eng)
             if need_grad:
                 logits, loss = _Step.apply(self._anchor, self, pl)
             else:

@@ -37,9 +37,10 @@ def core_config() -> Dict:
 
 
 def tiny_core_config() -> Dict:
-    """Same structure, sizes small enough for a committed fixture (heads stay 64 wide)."""
+    """Same structure, sizes small enough for a committed fixture (heads stay 64 wide; hidden 256 = the narrowest row the
+    row-wise kernels take)."""
     c = core_config()
-    c.update({"hidden_size": 128, "num_attention_heads": 2, "intermediate_size": 256, "v_feature_size": 64,
+    c.update({"hidden_size": 256, "num_attention_heads": 4, "intermediate_size": 512, "v_feature_size": 64,
               "v_num_hidden_layers": 2, "t_num_hidden_layers": 4, "num_co_layers": 2, "max_regions": 40, "vocab_size": 500,
               "max_position_embeddings": 64})
     return c

@@ -170,8 +170,29 @@ def dropout(x, y, p, site, seed):
     return y
 
 
-def seed_advance(seed):
-    pass
+def seed_advance(seed, snapshot=None):
+    seed.mul_(6364136223846793005).add_(1442695040888963407)     # int64 wrap-around = the kernel's uint64 LCG
+    if snapshot is not None:
+        snapshot.copy_(seed)
+
+
+def stage_batch(segs, err_flag=None):
+    """vb_stage_batch: range-checked index conversion (ignore_index -100 legal for labels), mask -> additive bias, feature
+    rounding, box copy; violations OR their bit into the flag and store `lo`."""
+    from multimodal_classification_b200 import _lib as L
+    for kind, src, dst, lo, hi, bit in segs:
+        v = src.reshape(-1)
+        if kind == L.STAGE_INDEX:
+            ok = (v >= lo) & (v < hi)
+            if bit == L.STAGE_ERR_LABEL:
+                ok |= v == L.IGNORE_INDEX
+            if err_flag is not None and not bool(ok.all()):
+                err_flag._host[0] |= bit
+            dst.view(-1).copy_(torch.where(ok, v, torch.full_like(v, lo)))
+        elif kind == L.STAGE_MASK:
+            dst.view(-1).copy_((1.0 - v.float()) * -10000.0)
+        else:
+            dst.view(-1).copy_(v)
 
 
 def act_bwd(dy, y, dx, act):
@@ -195,14 +216,16 @@ def cls_ce_fwd(h, w, bias, labels, logits, probs, loss):
     z = h.float() @ w.t() + bias
     logits.copy_(z)
     probs.copy_(torch.softmax(z, -1))
-    loss.fill_(0.0 if labels is None else F.cross_entropy(z, labels.long()).item())
+    loss.fill_(0.0 if labels is None else F.cross_entropy(z, labels.long()).item())     # ignore_index = -100, as the kernel
 
 
 def cls_ce_bwd(h, w, labels, probs, dloss, dlogits_ext, dw, db, dh):
     bsz = probs.shape[0]
     dz = dlogits_ext.clone() if dlogits_ext is not None else torch.zeros_like(probs)
     if labels is not None:
-        dz = dz + dloss * (probs - F.one_hot(labels.long(), probs.shape[1]).float()) / bsz
+        valid = (labels != -100)
+        onehot = F.one_hot(labels.long().clamp(min=0), probs.shape[1]).float()
+        dz = dz + dloss * (probs - onehot) * valid[:, None].float() / valid.sum()
     dw.copy_(dz.t() @ h.float())
     db.copy_(dz.sum(0))
     dh.copy_(dz @ w)
@@ -302,7 +325,7 @@ def nms(boxes, scores, iou_threshold):
 ROI_SIMULATED = ["stem_im2col", "im2col_nhwc", "maxpool_nhwc", "roi_pool_nhwc", "roi_align_nhwc", "avgpool_nhwc", "box_area_score",
                  "nms"]
 SIMULATED = ["gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "colsum", "cast_bf16", "cast_f32", "mask_bias",
-             "i64_to_i32", "dropout", "seed_advance", "act_bwd", "loc_embed_fwd", "loc_embed_bwd", "cls_ce_fwd", "cls_ce_bwd",
+             "i64_to_i32", "stage_batch", "dropout", "seed_advance", "act_bwd", "loc_embed_fwd", "loc_embed_bwd", "cls_ce_fwd", "cls_ce_bwd",
              "attention_fwd", "attention_bwd"]
 
 

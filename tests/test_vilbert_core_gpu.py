@@ -1,7 +1,6 @@
-"""First B200 parity run of the vilbert_core surface (multimodal_classification_b200/vilbert_core.py).  Its schedule is
-verified in the CPU suite (tests/test_vilbert_core_cpu.py); this file is the GPU half and is opt-in (VB_RUN_CORE_GPU=1) until
-it has been run once on a B200 — the round that wrote it had no GPU minutes left, and an untested GEMM shape that trapped
-would take the rest of the GPU suite down with it."""
+"""B200 parity of the vilbert_core surface (multimodal_classification_b200/vilbert_core.py; reference
+models/vilbert_core.py:593-657) against the reference-made fixture and the pinned oracle.  Its host schedule is also verified in
+the CPU suite (tests/test_vilbert_core_cpu.py)."""
 import os
 
 import numpy as np
@@ -10,8 +9,7 @@ import torch
 
 from oracle import vilbert_core_oracle as co
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("VB_RUN_CORE_GPU", "0") != "1",
-                                                  reason="first B200 run pending: set VB_RUN_CORE_GPU=1")]
+pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "vilbert_core_tiny.npz"))
 
 
