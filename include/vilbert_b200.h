@@ -81,6 +81,9 @@ int vb_gemm_bf16(const vb_gemm_args* args, void* stream);
  * stamps (entry, prologue done, dependency wait done, first load, loads done, first operands landed, MMAs issued, first /
  * last accumulator ready, stores issued, staging drained, exit) to device_buffer[cta*24 ..].  NULL switches it off. */
 int vb_gemm_set_trace(void* device_buffer);
+/* Experiment knobs of the tile picker / kernel (the VB_GEMM_* environment variables, settable at run time by the profiling
+ * tools): "occ1", "max_bn", "np", "cg", "debug_mode", "stages", "no_l2_hints".  Not for production use. */
+int vb_gemm_set_knob(const char* name, int value);
 /* Diagnostic (tools/gemm_occupancy.py): resident blocks per SM and co-resident 2-CTA clusters the runtime reports for the
  * narrow-tile pair kernel at `smem_bytes` of dynamic shared memory. */
 int vb_gemm_debug_occupancy(int smem_bytes, int* blocks_per_sm, int* clusters);

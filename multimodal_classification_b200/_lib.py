@@ -117,6 +117,7 @@ def _declare(l: C.CDLL) -> None:
         "vb_embed_text_fwd": [C.POINTER(EmbedArgs), vp], "vb_embed_text_bwd": [C.POINTER(EmbedArgs), vp],
         "vb_attention_fwd": [C.POINTER(AttnArgs), vp], "vb_attention_bwd": [C.POINTER(AttnArgs), vp],
         "vb_gemm_set_trace": [vp],
+        "vb_gemm_set_knob": [C.c_char_p, i32],
         "vb_colsum_bf16": [vp, i64, i32, i32, vp, vp],
         "vb_cast_f32_bf16": [vp, vp, i64, vp],
         "vb_cast_bf16_f32": [vp, vp, i64, vp],

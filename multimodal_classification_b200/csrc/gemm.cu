@@ -28,6 +28,7 @@
 // launched with programmatic dependent launch.  See include/vilbert_b200.h for the ABI.
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "launch.h"
@@ -133,6 +134,57 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "mem
 // named barrier 1: the MMA warp (publishes the TMEM base address) + the epilogue warps (consume it)
 __device__ __forceinline__ void tmem_slot_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 + GEMM_EPI_WARPS * 32) : "memory"); }
 
+// Warp-collective forms for the producer: the WHOLE (converged) warp executes the call with warp-uniform operands and one
+// elected lane issues.  With `if (lane == 0) tma_load(...)` the operands live in per-lane registers and ptxas wraps every
+// UTMALDG in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop; the producer thread then spends ~500 cycles of dependent scalar
+// instructions per k-block (measured with tools/gemm_mainloop.py: the k-block time was ~520 cycles whatever the tile width,
+// the ring depth or whether any MMA was issued) -- more than the 256-cycle MMA time of a 128-wide tile.
+__device__ __forceinline__ void mbar_arrive_expect_tx_warp(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint64_t policy) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_mc_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+               " [%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint64_t policy) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
+// every lane polls (same barrier, same answer: no divergence), so the code after the wait is still warp-uniform
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if ((++spins & 1023u) == 0) {      // bounded by WALL CLOCK (2 s): see mbar_wait
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+
+// Epilogue kinds: the common ones are compiled as separate kernels so that a chunk's epilogue is ~100 straight-line
+// instructions with 32-wide instruction-level parallelism and no flag tests (two epilogue warps per scheduler cannot hide
+// branch / LDS latencies, and the code runs once per launch from a cold instruction cache); everything else takes the generic
+// kernel with run-time flags.
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_GELU_PRE = 2, EPI_AUX_ADD = 3, EPI_AUX_GELUGRAD = 4, EPI_F32 = 5 };
+
 // x / d for x * d < 2^32, d >= 1, with magic = ceil(2^32 / d) computed on the host (d = 1 -> magic 0 = "identity")
 __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return magic == 0u ? x : __umulhi(x, magic); }
 
@@ -145,31 +197,32 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKernelParams& p, int 
 }
 
 // Eight columns of the epilogue: v = acc * scale + bias (+ aux | * gelu'(aux)) -> activation -> one 16-byte (bf16) or two
-// 16-byte (fp32) pieces of the warp's staging box.  `g` = which eighth-of-a-chunk (0..3).
-__device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const uint32_t (&r)[8] /* 8 accumulator words */, int g,
+// 16-byte (fp32) pieces of the warp's staging box.  `g` = which eighth-of-a-chunk (0..3), a compile-time constant at every
+// call site (the chunk is unrolled).
+template <int EPI>
+__device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const uint32_t* r /* 8 accumulator words */, int g,
                                                uint32_t s_bias, uint32_t s_scale, const uint4& aux, uint32_t xrow, uint32_t orow,
                                                uint32_t swz64, uint32_t swz128) {
   float v[8];
-  const float4 b0 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u), b1 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u + 16u);
-  if (s_scale != 0u) {
-    const float4 s0 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u), s1 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u + 16u);
-    v[0] = fmaf(__uint_as_float(r[0]), s0.x, b0.x); v[1] = fmaf(__uint_as_float(r[1]), s0.y, b0.y);
-    v[2] = fmaf(__uint_as_float(r[2]), s0.z, b0.z); v[3] = fmaf(__uint_as_float(r[3]), s0.w, b0.w);
-    v[4] = fmaf(__uint_as_float(r[4]), s1.x, b1.x); v[5] = fmaf(__uint_as_float(r[5]), s1.y, b1.y);
-    v[6] = fmaf(__uint_as_float(r[6]), s1.z, b1.z); v[7] = fmaf(__uint_as_float(r[7]), s1.w, b1.w);
-  } else {
-    v[0] = __uint_as_float(r[0]) + b0.x; v[1] = __uint_as_float(r[1]) + b0.y;
-    v[2] = __uint_as_float(r[2]) + b0.z; v[3] = __uint_as_float(r[3]) + b0.w;
-    v[4] = __uint_as_float(r[4]) + b1.x; v[5] = __uint_as_float(r[5]) + b1.y;
-    v[6] = __uint_as_float(r[6]) + b1.z; v[7] = __uint_as_float(r[7]) + b1.w;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+  if constexpr (EPI == EPI_GENERIC) {
+    if (s_scale != 0u) {
+      const float4 s0 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u), s1 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u + 16u);
+      v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    }
   }
-  if (p.has_preact)
+  if constexpr (EPI == EPI_GENERIC || EPI == EPI_BIAS || EPI == EPI_GELU_PRE) {
+    const float4 b0 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u), b1 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u + 16u);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact))
     sts_u4(xrow + ((static_cast<uint32_t>(g) ^ swz64) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  if (p.aux_mode != VB_AUX_NONE) {
+  if (EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || (EPI == EPI_GENERIC && p.aux_mode != VB_AUX_NONE)) {
     const float2 a0 = unpack_bf16x2(aux.x), a1 = unpack_bf16x2(aux.y), a2 = unpack_bf16x2(aux.z), a3 = unpack_bf16x2(aux.w);
     const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-    if (p.aux_mode == VB_AUX_ADD) {
+    if (EPI == EPI_AUX_ADD || (EPI == EPI_GENERIC && p.aux_mode == VB_AUX_ADD)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] += av[i];
     } else {
@@ -177,17 +230,17 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
       for (int i = 0; i < 8; ++i) v[i] *= gelu_fast_grad(av[i]);
     }
   }
-  if (p.act == VB_ACT_GELU) {
+  if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.act == VB_ACT_GELU)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-  } else if (p.act == VB_ACT_RELU) {
+  } else if (EPI == EPI_GENERIC && p.act == VB_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
-  } else if (p.act == VB_ACT_TANH) {
+  } else if (EPI == EPI_GENERIC && p.act == VB_ACT_TANH) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i]);
   }
-  if (p.d_is_f32) {
+  if (EPI == EPI_F32 || (EPI == EPI_GENERIC && p.d_is_f32)) {
     // fp32 box: 32 columns = eight 16-byte pieces per 128-byte row (128B-swizzled); this octet is pieces 2g, 2g + 1
     sts_u4(orow + ((static_cast<uint32_t>(2 * g) ^ swz128) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
            __float_as_uint(v[3]));
@@ -200,67 +253,51 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
   }
 }
 
-// One k-block of operand loads (the producer's loop body).  `live = false` is the instruction-cache warm-up pass: the producer
-// walks the same code once with every TMA / mbarrier instruction predicated off WHILE it waits for the cluster barrier, so the
-// first real loads do not pay a chain of cold instruction-fetch misses (a 5 us kernel starts with an empty L0 / L1.5 I-cache).
+// One k-block of operand loads (the producer's loop body), executed by the whole producer warp with uniform operands.
 template <bool A_MN, bool B_MN, int CG, int NP>
-__device__ __forceinline__ void issue_kblock(const CUtensorMap* tma_a, const CUtensorMap* tma_b, uint8_t* sa, uint8_t* sb,
-                                             uint64_t* full_bar, uint32_t bar_leader, int bnl, int k0, int m0, int n0,
-                                             uint32_t prank, uint32_t pair, uint16_t a_mask, unsigned long long b_policy, bool live) {
+__device__ __forceinline__ void issue_kblock(const CUtensorMap* tma_a, const CUtensorMap* tma_b, uint32_t sa, uint32_t sb,
+                                             uint32_t full_bar, uint32_t bar_leader, int bnl, int k0, int m0, int n0,
+                                             uint32_t prank, uint32_t pair, uint16_t a_mask, unsigned long long b_policy) {
   const int b_bytes = bnl * GEMM_BK * 2;
   if constexpr (CG == 2) {
     // both CTAs' bytes are counted on the leader's barrier; a peer load that lands before the leader's expect_tx only
     // drives the transaction count negative for a moment (same phase: the peer cannot run ahead of the leader's MMA,
     // which frees the stage for both)
-    if (live && prank == 0) mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(2 * (GEMM_A_BYTES + b_bytes)));
+    if (prank == 0) mbar_arrive_expect_tx_warp(full_bar, static_cast<uint32_t>(2 * (GEMM_A_BYTES + b_bytes)));
     if constexpr (NP == 2) {
       // the two pairs of the cluster work on the same 256 rows: each CTA fetches HALF of its A tile (64 rows) and
       // multicasts it to itself and to its twin in the other pair, which halves the A bytes read from L2.  Safe:
       // empty_bar counts the commits of BOTH pairs, so the twin's slot is free too.
-      if (live) {
-        if constexpr (A_MN) tma_load_2d_pair_mc(sa + pair * (GEMM_BK * 128), tma_a, bar_leader, m0 + static_cast<int>(pair) * 64, k0, a_mask);
-        else                tma_load_2d_pair_mc(sa + pair * (64 * 128), tma_a, bar_leader, k0, m0 + static_cast<int>(pair) * 64, a_mask);
-      }
+      if constexpr (A_MN) tma_load_2d_pair_mc_warp(sa + pair * (GEMM_BK * 128), tma_a, bar_leader, m0 + static_cast<int>(pair) * 64, k0, a_mask);
+      else                tma_load_2d_pair_mc_warp(sa + pair * (64 * 128), tma_a, bar_leader, k0, m0 + static_cast<int>(pair) * 64, a_mask);
     } else if constexpr (A_MN) {
 #pragma unroll
-      for (int j = 0; j < GEMM_BM / 64; ++j)
-        if (live) tma_load_2d_pair(sa + j * (GEMM_BK * 128), tma_a, bar_leader, m0 + j * 64, k0);
+      for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair_warp(sa + j * (GEMM_BK * 128), tma_a, bar_leader, m0 + j * 64, k0, L2_EVICT_NORMAL);
     } else {
-      if (live) tma_load_2d_pair(sa, tma_a, bar_leader, k0, m0);
+      tma_load_2d_pair_warp(sa, tma_a, bar_leader, k0, m0, L2_EVICT_NORMAL);
     }
     if constexpr (B_MN) {
-      for (int j = 0; j < bnl / 64; ++j) {
-        if (!live) continue;
-        if (b_policy) tma_load_2d_pair_hint(sb + j * (GEMM_BK * 128), tma_b, bar_leader, n0 + j * 64, k0, b_policy);
-        else          tma_load_2d_pair(sb + j * (GEMM_BK * 128), tma_b, bar_leader, n0 + j * 64, k0);
-      }
-    } else if (live) {
-      if (b_policy) tma_load_2d_pair_hint(sb, tma_b, bar_leader, k0, n0, b_policy);
-      else          tma_load_2d_pair(sb, tma_b, bar_leader, k0, n0);
+      for (int j = 0; j < bnl / 64; ++j) tma_load_2d_pair_warp(sb + j * (GEMM_BK * 128), tma_b, bar_leader, n0 + j * 64, k0, b_policy);
+    } else {
+      tma_load_2d_pair_warp(sb, tma_b, bar_leader, k0, n0, b_policy);
     }
   } else {
-    if (live) mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(GEMM_A_BYTES + b_bytes));
+    mbar_arrive_expect_tx_warp(full_bar, static_cast<uint32_t>(GEMM_A_BYTES + b_bytes));
     if constexpr (A_MN) {
 #pragma unroll
-      for (int j = 0; j < GEMM_BM / 64; ++j)
-        if (live) tma_load_2d(sa + j * (GEMM_BK * 128), tma_a, full_bar, m0 + j * 64, k0);
+      for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_warp(sa + j * (GEMM_BK * 128), tma_a, full_bar, m0 + j * 64, k0, L2_EVICT_NORMAL);
     } else {
-      if (live) tma_load_2d(sa, tma_a, full_bar, k0, m0);
+      tma_load_2d_warp(sa, tma_a, full_bar, k0, m0, L2_EVICT_NORMAL);
     }
     if constexpr (B_MN) {
-      for (int j = 0; j < bnl / 64; ++j) {
-        if (!live) continue;
-        if (b_policy) tma_load_2d_hint(sb + j * (GEMM_BK * 128), tma_b, full_bar, n0 + j * 64, k0, b_policy);
-        else          tma_load_2d(sb + j * (GEMM_BK * 128), tma_b, full_bar, n0 + j * 64, k0);
-      }
-    } else if (live) {
-      if (b_policy) tma_load_2d_hint(sb, tma_b, full_bar, k0, n0, b_policy);
-      else          tma_load_2d(sb, tma_b, full_bar, k0, n0);
+      for (int j = 0; j < bnl / 64; ++j) tma_load_2d_warp(sb + j * (GEMM_BK * 128), tma_b, full_bar, n0 + j * 64, k0, b_policy);
+    } else {
+      tma_load_2d_warp(sb, tma_b, full_bar, k0, n0, b_policy);
     }
   }
 }
 
-template <bool A_MN, bool B_MN, int CG, int NP, int OCC>
+template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, OCC)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_x,
@@ -336,48 +373,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int tile_step = gridDim.x / CS;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one per CTA)
+    // ------------------------------------------------------------------ TMA producer (one per CTA; warp-uniform code)
     const uint32_t full_leader = CG == 2 ? mapa_u32(&full_bar[0], leader_rank) : 0u;
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
     const uint16_t a_mask = static_cast<uint16_t>((1u << prank) | (1u << (prank + 2)));   // me and my twin in the other pair
-    if (lane == 0) {
-      // warm-up pass over the issue code (nothing is issued), see issue_kblock
-      const TileCoord tc = decode_tile(p, first_tile);
-      issue_kblock<A_MN, B_MN, CG, NP>(&tma_a, &tma_b, smem_a, smem_b, &full_bar[0], full_leader, BNL, 0,
-                                       tc.m_idx * (GEMM_BM * CG), tc.n_idx * BN, prank, pair, a_mask, p.b_policy, false);
-    }
-    __syncwarp();
+    const unsigned long long b_policy = p.b_policy ? p.b_policy : L2_EVICT_NORMAL;
     if constexpr (CS > 1) cluster_wait(); else cta_sync();
     if (lane == 0) trace_stamp(1);
     griddep_wait();     // operands written by the previous kernel of the stream are complete and visible from here on
-    if (lane == 0) {
-      trace_stamp(2);
-      int stage = 0, fills = 0;
-      uint32_t phase = 0;
-      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
-        const TileCoord tc = decode_tile(p, tile);
-        const int m0 = tc.m_idx * (GEMM_BM * CG) + static_cast<int>(prank) * GEMM_BM;
-        const int n0 = (tc.n_idx * NP + static_cast<int>(pair)) * BN + static_cast<int>(prank) * BNL;
-        const int kb0 = tc.split * p.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          if (fills >= STAGES) mbar_wait(&empty_bar[stage], phase ^ 1u);   // the first pass over the ring needs no wait
-          ++fills;
+    if (lane == 0) trace_stamp(2);
+    int stage = 0, fills = 0;
+    uint32_t phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int m0 = tc.m_idx * (GEMM_BM * CG) + static_cast<int>(prank) * GEMM_BM;
+      const int n0 = (tc.n_idx * NP + static_cast<int>(pair)) * BN + static_cast<int>(prank) * BNL;
+      const int kb0 = tc.split * p.kb_per_split;
+      const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        if (fills >= STAGES) mbar_wait_addr(empty0 + static_cast<uint32_t>(stage) * 8u, phase ^ 1u);   // the first pass over the ring needs no wait
+        ++fills;
 #ifdef VB_GEMM_TRACE
-          if (p.debug_mode == 2) {
-            if (prank == 0) mbar_arrive(&full_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            continue;
-          }
-#endif
-          issue_kblock<A_MN, B_MN, CG, NP>(&tma_a, &tma_b, smem_a + stage * GEMM_A_BYTES, smem_b + stage * B_BYTES, &full_bar[stage],
-                                           full_leader + static_cast<uint32_t>(stage) * 8u, BNL, kb * GEMM_BK, m0, n0, prank, pair,
-                                           a_mask, p.b_policy, true);
-          if (tile == first_tile && kb == kb0) trace_stamp(3);
+        if (p.debug_mode == 2) {
+          if (prank == 0 && lane == 0) mbar_arrive(&full_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          continue;
         }
+#endif
+        issue_kblock<A_MN, B_MN, CG, NP>(&tma_a, &tma_b, sa0 + static_cast<uint32_t>(stage * GEMM_A_BYTES),
+                                         sb0 + static_cast<uint32_t>(stage * B_BYTES), full0 + static_cast<uint32_t>(stage) * 8u,
+                                         full_leader + static_cast<uint32_t>(stage) * 8u, BNL, kb * GEMM_BK, m0, n0, prank, pair,
+                                         a_mask, b_policy);
+        if (lane == 0 && tile == first_tile && kb == kb0) trace_stamp(3);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      trace_stamp(4);
     }
+    if (lane == 0) trace_stamp(4);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ TMEM owner + MMA issuer (the leader CTA of every pair)
     if constexpr (CG == 2) {
@@ -492,81 +525,86 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
       __syncwarp();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
-      // One octet (8 columns) per iteration of a ROLLED loop: the body is ~1 KB of code that stays in the instruction cache,
-      // where a chunk-wide unrolled epilogue spent most of its time on instruction fetch (it runs once, straight after a
-      // kernel switch).  TMEM loads and aux reads run one octet ahead of the arithmetic.  Iteration -1 of the CTA's first tile
-      // is a dry run on zeros, executed while the main loop is still computing: it pulls the body into the cache.
-      uint32_t r_cur[8], r_nxt[8];
-      uint4 a_cur = make_uint4(0u, 0u, 0u, 0u), a_nxt = make_uint4(0u, 0u, 0u, 0u);
+      // One 32-column chunk per iteration: the accumulator words arrive with ONE tcgen05.ld (a TMEM load has ~300 cycles of
+      // latency whatever its width: 8-column loads in a rolled loop were 2x slower), the chunk is processed by straight-line
+      // code specialised at compile time, and the NEXT chunk's TMEM load and aux reads are issued before the current chunk is
+      // staged and stored.  Iteration -1 of the CTA's first tile is a dry run on zeros while the main loop is still computing:
+      // it pulls the epilogue code into the instruction cache (nothing is stored).
+      constexpr bool HAS_AUX = EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_GENERIC;
+      const int my_chunks = (nch - half + 1) / 2;
+      uint32_t r[32];
+      uint4 a_cur[4], a_nxt[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { r_cur[i] = 0u; r_nxt[i] = 0u; }
+      for (int i = 0; i < 32; ++i) r[i] = 0u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a_cur[i] = make_uint4(0u, 0u, 0u, 0u); a_nxt[i] = make_uint4(0u, 0u, 0u, 0u); }
       const bool warm = tile == first_tile;
 #pragma unroll 1
-      for (int o = -1; o < n_oct; ++o) {
-        const bool live = o >= 0;
-        const int oo = live ? o : 3;
-        const int j = oo >> 2, g = oo & 3;
-        const int c = half + 2 * j;
-        if (live && o + 1 < n_oct) {
-          const int o1 = o + 1, c1 = half + 2 * (o1 >> 2), col1 = c1 * GEMM_CHUNK + (o1 & 3) * 8;
-          tmem_ld_32x8(taddr + static_cast<uint32_t>(col1), r_nxt);
-          if (has_aux) a_nxt = (aux_row != nullptr && n0 + col1 < p.n) ? ldg_nc_u4(aux_row + n0 + col1) : make_uint4(0u, 0u, 0u, 0u);
-        }
-        if (live || warm) {
-          if (live && g == 0) {
-            if (lane == 0) tma_store_wait_read();   // my staging box(es) of the previous chunk have been read by the TMA engine
-            __syncwarp();
-          }
-          epilogue_octet(p, r_cur, g, sa_bias + static_cast<uint32_t>(j * GEMM_CHUNK) * 4u,
-                         sa_scale != 0u ? sa_scale + static_cast<uint32_t>(j * GEMM_CHUNK) * 4u : 0u, a_cur, xrow, orow, swz64, swz128);
-          if (g == 3) {
-            fence_proxy_async_smem();           // make the staged box visible to the TMA engine
-            __syncwarp();
-            const int c0 = n0 + c * GEMM_CHUNK;
-            if (live && lane == 0 && c0 < p.n && r0 < p.m) {
-              if (p.d_is_f32) {
-                if (p.d_policy) {
-                  if (p.reduce_add) tma_reduce_add_2d_hint(&tma_d, box_out, c0, r0, p.d_policy);
-                  else              tma_store_2d_hint(&tma_d, box_out, c0, r0, p.d_policy);
-                } else {
-                  if (p.reduce_add) tma_reduce_add_2d(&tma_d, box_out, c0, r0);
-                  else              tma_store_2d(&tma_d, box_out, c0, r0);
-                }
-              } else {
-                tma_store_2d(&tma_d, box_out, c0, r0);
-                if (p.has_preact) tma_store_2d(&tma_x, box_x, c0, r0);
-              }
-              tma_store_commit();
-              if (tracer && j == 0) trace_stamp(16);
+      for (int j = warm ? -1 : 0; j < my_chunks; ++j) {
+        const bool live = j >= 0;
+        const int jj = live ? j : 0;
+        const int c = half + 2 * jj;
+        if (j == 0) {
+          // the accumulator of this tile: first aux reads are already in flight when the wait returns
+          if (HAS_AUX && has_aux) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = n0 + c * GEMM_CHUNK + 8 * q;
+              a_cur[q] = (aux_row != nullptr && col < p.n) ? ldg_nc_u4(aux_row + col) : make_uint4(0u, 0u, 0u, 0u);
             }
-            if (tracer && live && j == 0) trace_stamp(13);
           }
-        }
-        if (!live) {
-          // the accumulator of this tile: wait for it, then start the one-octet-ahead pipeline
-          if (has_aux) a_nxt = (aux_row != nullptr && n0 + half * GEMM_CHUNK < p.n) ? ldg_nc_u4(aux_row + n0 + half * GEMM_CHUNK)
-                                                                                     : make_uint4(0u, 0u, 0u, 0u);
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tc_fence_after();
           if (tracer && tile == first_tile) trace_stamp(7);
           if (tracer) trace_stamp(8);     // last tile's accumulator ready
-          tmem_ld_32x8(taddr + static_cast<uint32_t>(half * GEMM_CHUNK), r_nxt);
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c * GEMM_CHUNK), r);
         }
-        tmem_ld_wait();
-        if (tracer && o == -1) trace_stamp(12);
-        if (o + 2 == n_oct) {
-          // my share of the accumulator stage is in registers (the load of my last octet has completed): hand the stage back
-          // to the MMA warp (of the leader) right away
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + static_cast<uint32_t>(acc) * 8u);
-            else                   mbar_arrive(&tmem_empty_bar[acc]);
-          }
-        }
+        if (live) {
+          if (HAS_AUX && has_aux && j + 1 < my_chunks) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r_cur[i] = r_nxt[i];
-        a_cur = a_nxt;
+            for (int q = 0; q < 4; ++q) {
+              const int col = n0 + (c + 2) * GEMM_CHUNK + 8 * q;
+              a_nxt[q] = (aux_row != nullptr && col < p.n) ? ldg_nc_u4(aux_row + col) : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          tmem_ld_wait();
+          if (tracer && j == 0) trace_stamp(12);
+          if (j + 1 == my_chunks) {
+            // my share of the accumulator stage is in registers: hand the stage back to the MMA warp (of the leader) right away
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + static_cast<uint32_t>(acc) * 8u);
+              else                   mbar_arrive(&tmem_empty_bar[acc]);
+            }
+          }
+          if (lane == 0) tma_store_wait_read();   // my staging box(es) of the previous chunk have been read by the TMA engine
+          __syncwarp();
+        }
+        const uint32_t sb = sa_bias + static_cast<uint32_t>(jj * GEMM_CHUNK) * 4u;
+        const uint32_t ss = sa_scale != 0u ? sa_scale + static_cast<uint32_t>(jj * GEMM_CHUNK) * 4u : 0u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) epilogue_octet<EPI>(p, &r[8 * g], g, sb, ss, a_cur[g], xrow, orow, swz64, swz128);
+        if (live && j + 1 < my_chunks) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * GEMM_CHUNK), r);   // r is free again
+        if (tracer && live && j == 0) trace_stamp(13);
+        fence_proxy_async_smem();           // make the staged box visible to the TMA engine
+        __syncwarp();
+        const int c0 = n0 + c * GEMM_CHUNK;
+        if (live && lane == 0 && c0 < p.n && r0 < p.m) {
+          if (EPI == EPI_F32 || (EPI == EPI_GENERIC && p.d_is_f32)) {
+            if (p.reduce_add) tma_reduce_add_2d_hint(&tma_d, box_out, c0, r0, p.d_policy ? p.d_policy : L2_EVICT_NORMAL);
+            else              tma_store_2d_hint(&tma_d, box_out, c0, r0, p.d_policy ? p.d_policy : L2_EVICT_NORMAL);
+          } else {
+            tma_store_2d(&tma_d, box_out, c0, r0);
+            if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact)) tma_store_2d(&tma_x, box_x, c0, r0);
+          }
+          tma_store_commit();
+          if (tracer && j == 0) trace_stamp(16);
+        }
+        if (HAS_AUX && live) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a_cur[q] = a_nxt[q];
+        }
       }
       if (++acc == GEMM_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
@@ -616,10 +654,15 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static bool occ1_forced() {
-  static const bool v = getenv("VB_GEMM_OCC1") != nullptr && atoi(getenv("VB_GEMM_OCC1")) != 0;
-  return v;
+// experiment knobs: read once from the environment, overridable at run time through vb_gemm_set_knob (tools/gemm_mainloop.py)
+struct GemmKnobs { int occ1, max_bn, np, cg, debug_mode, stages, no_l2_hints; };
+static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+static GemmKnobs& knobs() {
+  static GemmKnobs k = {env_int("VB_GEMM_OCC1", 0), env_int("VB_GEMM_MAX_BN", 256), env_int("VB_GEMM_NP", 0), env_int("VB_GEMM_CG", 0),
+                        env_int("VB_GEMM_DEBUG", 0), env_int("VB_GEMM_STAGES", 0), env_int("VB_GEMM_NO_L2_HINTS", 0)};
+  return k;
 }
+static bool occ1_forced() { return knobs().occ1 != 0; }
 static int gemm_occupancy(int bn) { return (bn <= 128 && !occ1_forced()) ? 2 : 1; }
 
 // Co-resident clusters of `cs` CTAs (one CTA per SM).  Clusters cannot straddle a GPC and the B200's GPCs do not all hold a
@@ -643,21 +686,21 @@ static int max_clusters(int cs, int occupancy) {
     cudaError_t e;
     if (occupancy == 2) {
       if (cs == 2) {
-        auto kern = gemm_bf16_kernel<false, false, 2, 1, 2>;
+        auto kern = gemm_bf16_kernel<false, false, 2, 1, 2, EPI_GENERIC>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_limit(2));
         e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
       } else {
-        auto kern = gemm_bf16_kernel<false, false, 2, 2, 2>;
+        auto kern = gemm_bf16_kernel<false, false, 2, 2, 2, EPI_GENERIC>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_limit(2));
         e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
       }
     } else {
       if (cs == 2) {
-        auto kern = gemm_bf16_kernel<false, false, 2, 1, 1>;
+        auto kern = gemm_bf16_kernel<false, false, 2, 1, 1, EPI_GENERIC>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_limit(1));
         e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
       } else {
-        auto kern = gemm_bf16_kernel<false, false, 2, 2, 1>;
+        auto kern = gemm_bf16_kernel<false, false, 2, 2, 1, EPI_GENERIC>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_limit(1));
         e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
       }
@@ -677,7 +720,7 @@ static int gemm_stages(int bn, int cg, bool f32, bool preact, bool has_scale) {
   return stages;
 }
 
-template <bool A_MN, bool B_MN, int CG, int NP, int OCC>
+template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI>
 static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t stream) {
   constexpr int CS = CG * NP;
   const int bnl = bn / CG;
@@ -729,11 +772,10 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
     vb_set_last_error("vb_gemm_bf16", "tile configuration does not fit shared memory");
     return VB_ERR_UNSUPPORTED;
   }
-  static const int debug_mode = getenv("VB_GEMM_DEBUG") ? atoi(getenv("VB_GEMM_DEBUG")) : 0;
-  static const int debug_stages = getenv("VB_GEMM_STAGES") ? atoi(getenv("VB_GEMM_STAGES")) : 0;
-  p.debug_mode = debug_mode;
+  const int debug_stages = knobs().stages;
+  p.debug_mode = knobs().debug_mode;
   p.trace = g_trace;
-  static const bool hints = !(getenv("VB_GEMM_NO_L2_HINTS") && atoi(getenv("VB_GEMM_NO_L2_HINTS")) != 0);
+  const bool hints = knobs().no_l2_hints == 0;
   p.b_policy = (hints && a.b_streamed) ? L2_EVICT_FIRST : 0ull;     // 0 = the plain (un-hinted) instruction
   p.d_policy = (hints && a.d_streamed && a.d_is_f32) ? L2_EVICT_FIRST : 0ull;
   if (debug_stages >= 2 && debug_stages < stages) stages = debug_stages;
@@ -744,7 +786,7 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   const int smem_bytes = 1024 + static_cast<int>(L.total);
 
   static bool attr_set = false;   // one per instantiation
-  auto kern = gemm_bf16_kernel<A_MN, B_MN, CG, NP, OCC>;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, CG, NP, OCC, EPI>;
   if (!attr_set) {
     VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_limit(OCC)));
     attr_set = true;
@@ -787,8 +829,7 @@ static double tile_cost(const vb_gemm_args& a, int bn, int cg, int np, int kb, d
 }
 
 static bool tile_legal(const vb_gemm_args& a, int bn, int cg) {
-  static const int max_bn = getenv("VB_GEMM_MAX_BN") ? atoi(getenv("VB_GEMM_MAX_BN")) : 256;   // experiments: compact tiles only
-  if (bn > max_bn) return false;
+  if (bn > knobs().max_bn) return false;   // experiments: compact tiles only
   if (cg == 1) return bn == 64 || bn == 128;
   if (a.b_mn_major) return bn == 128 || bn == 256;              // 64-wide MN pieces per CTA
   if (a.a_mn_major) return bn == 128;                           // (MN, K): API completeness only
@@ -796,8 +837,7 @@ static bool tile_legal(const vb_gemm_args& a, int bn, int cg) {
 }
 
 static TileChoice pick_config(const vb_gemm_args& a) {
-  static const int force_np = getenv("VB_GEMM_NP") ? atoi(getenv("VB_GEMM_NP")) : 0;
-  static const int force_cg = getenv("VB_GEMM_CG") ? atoi(getenv("VB_GEMM_CG")) : 0;
+  const int force_np = knobs().np, force_cg = knobs().cg;
   const int total_kb = (a.k + GEMM_BK - 1) / GEMM_BK;
   const bool can_split = a.d_is_f32 && a.accumulate;
   double best_cost = 1e30;
@@ -837,12 +877,38 @@ static TileChoice pick_config(const vb_gemm_args& a) {
   return best;
 }
 
+// Which compiled epilogue serves this call (anything unusual -> the generic kernel with run-time flags)
+static int pick_epilogue(const vb_gemm_args& a) {
+  static const bool generic_only = env_int("VB_GEMM_GENERIC_EPI", 0) != 0;
+  if (generic_only || a.scale != nullptr) return EPI_GENERIC;
+  if (a.d_is_f32) return (a.bias == nullptr && a.act == VB_ACT_NONE && a.aux_mode == VB_AUX_NONE) ? EPI_F32 : EPI_GENERIC;
+  if (a.d_preact != nullptr) return (a.act == VB_ACT_GELU && a.aux_mode == VB_AUX_NONE) ? EPI_GELU_PRE : EPI_GENERIC;
+  if (a.aux_mode != VB_AUX_NONE)
+    return (a.bias == nullptr && a.act == VB_ACT_NONE) ? (a.aux_mode == VB_AUX_ADD ? EPI_AUX_ADD : EPI_AUX_GELUGRAD) : EPI_GENERIC;
+  return a.act == VB_ACT_NONE ? EPI_BIAS : EPI_GENERIC;
+}
+
+// Instantiated combinations: the specialised epilogues only for the operand layouts the training step uses them with
+// (forward K-major/K-major, dgrad K-major/MN-major, wgrad MN-major/MN-major) and only for CTA pairs; everything else is generic.
 template <int CG, int NP, int OCC>
 static int dispatch_major(const vb_gemm_args& a, int bn, int splits, cudaStream_t s) {
-  if (a.a_mn_major && a.b_mn_major) return launch_gemm<true, true, CG, NP, OCC>(a, bn, splits, s);
-  if (a.a_mn_major) return launch_gemm<true, false, CG, NP, OCC>(a, bn, splits, s);
-  if (a.b_mn_major) return launch_gemm<false, true, CG, NP, OCC>(a, bn, splits, s);
-  return launch_gemm<false, false, CG, NP, OCC>(a, bn, splits, s);
+  const int epi = CG == 2 ? pick_epilogue(a) : EPI_GENERIC;
+  if constexpr (CG == 2) {
+    if (!a.a_mn_major && !a.b_mn_major) {
+      if (epi == EPI_BIAS) return launch_gemm<false, false, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);
+      if (epi == EPI_GELU_PRE) return launch_gemm<false, false, CG, NP, OCC, EPI_GELU_PRE>(a, bn, splits, s);
+    } else if (!a.a_mn_major && a.b_mn_major) {
+      if (epi == EPI_BIAS) return launch_gemm<false, true, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);
+      if (epi == EPI_AUX_ADD) return launch_gemm<false, true, CG, NP, OCC, EPI_AUX_ADD>(a, bn, splits, s);
+      if (epi == EPI_AUX_GELUGRAD) return launch_gemm<false, true, CG, NP, OCC, EPI_AUX_GELUGRAD>(a, bn, splits, s);
+    } else if (a.a_mn_major && a.b_mn_major) {
+      if (epi == EPI_F32) return launch_gemm<true, true, CG, NP, OCC, EPI_F32>(a, bn, splits, s);
+    }
+  }
+  if (a.a_mn_major && a.b_mn_major) return launch_gemm<true, true, CG, NP, OCC, EPI_GENERIC>(a, bn, splits, s);
+  if (a.a_mn_major) return launch_gemm<true, false, CG, NP, OCC, EPI_GENERIC>(a, bn, splits, s);
+  if (a.b_mn_major) return launch_gemm<false, true, CG, NP, OCC, EPI_GENERIC>(a, bn, splits, s);
+  return launch_gemm<false, false, CG, NP, OCC, EPI_GENERIC>(a, bn, splits, s);
 }
 
 template <int CG, int NP>
@@ -856,7 +922,7 @@ static int dispatch_occ(const vb_gemm_args& a, const TileChoice& c, cudaStream_t
 // diagnostic: resident blocks per SM / co-resident 2-CTA clusters the runtime reports for the compact pair kernel at a given
 // dynamic shared-memory size (tools/gemm_occupancy.py)
 extern "C" int vb_gemm_debug_occupancy(int smem_bytes, int* blocks_per_sm, int* clusters) {
-  auto kern = vb::gemm_bf16_kernel<false, false, 2, 1, 2>;
+  auto kern = vb::gemm_bf16_kernel<false, false, 2, 1, 2, vb::EPI_GENERIC>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, vb::GEMM_THREADS, smem_bytes) != cudaSuccess) return VB_ERR_CUDA;
@@ -871,6 +937,17 @@ extern "C" int vb_gemm_debug_occupancy(int smem_bytes, int* blocks_per_sm, int* 
   cudaFuncGetAttributes(&fa, kern);
   fprintf(stderr, "regs %d static smem %zu maxDyn %d\n", fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
   return VB_OK;
+}
+
+extern "C" int vb_gemm_set_knob(const char* name, int value) {
+  using namespace vb;
+  GemmKnobs& k = knobs();
+  const struct { const char* n; int* v; } tab[] = {{"occ1", &k.occ1}, {"max_bn", &k.max_bn}, {"np", &k.np}, {"cg", &k.cg},
+                                                   {"debug_mode", &k.debug_mode}, {"stages", &k.stages}, {"no_l2_hints", &k.no_l2_hints}};
+  for (const auto& e : tab)
+    if (strcmp(e.n, name) == 0) { *e.v = value; return VB_OK; }
+  vb_set_last_error("vb_gemm_set_knob", "unknown knob");
+  return VB_ERR_BAD_ARG;
 }
 
 extern "C" int vb_gemm_set_trace(void* device_buffer) {

@@ -18,10 +18,18 @@ def install(ingest: bool = True) -> None:
     from .resnet152_roi import ResNet152ROIExtractor
     from .resnet_grid import ResNetFeatureExtractor, ResNetVGExtractor
     from .vilbert import ViLBERTForClassification, get_facebook_vilbert_config, load_facebook_weights
+    from . import vilbert_core as core
 
     M.ViLBERTFacebookArch = A.ViLBERTForClassification = ViLBERTForClassification
     M.get_facebook_vilbert_config = A.get_facebook_vilbert_config = get_facebook_vilbert_config
     M.load_facebook_weights = A.load_facebook_weights = load_facebook_weights
+    # the second two-stream surface (models/vilbert_core.py:593-657; `ViLBERTCore` in models/__init__.py): same engine
+    import multimodalclassification.models.vilbert_core as VC
+    VC.ViLBERTForClassification = core.ViLBERTForClassification
+    VC.get_vilbert_config = core.get_vilbert_config
+    for name in ("ViLBERTCore", "ViLBERTCoreForClassification"):
+        if hasattr(M, name):
+            setattr(M, name, core.ViLBERTForClassification)
     FE.ResNet152ROIExtractor = ResNet152ROIExtractor
     B.FEATURE_EXTRACTOR_REGISTRY["resnet152_roi"] = ResNet152ROIExtractor
     FE.ResNetFeatureExtractor = ResNetFeatureExtractor                 # "resnet" in the same dict literal / registry

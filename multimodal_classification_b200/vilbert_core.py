@@ -18,9 +18,9 @@ visual stream are ``biattention_v.self.query`` and ``biattention_t.self.{key,val
 the engine under the Facebook layout's names, so the flat buffers, fused q|k|v GEMMs, graphs, gradient buckets and the fused
 optimizer apply unchanged.
 
-STATUS: the schedule is verified against the pinned oracle in the GPU-less container over the functional kernel stand-ins
-(tests/test_vilbert_core_cpu.py); its first parity run on a B200 is pending, so ``dropin.install()`` does not bind it yet.
-CUDA only, no fall-back.
+STATUS: verified against the reference-made fixture and the pinned oracle on the B200 (tests/test_vilbert_core_gpu.py) and, for
+the host schedule, in the GPU-less container over the functional kernel stand-ins (tests/test_vilbert_core_cpu.py);
+``dropin.install()`` binds it.  CUDA only, no fall-back.
 """
 from __future__ import annotations
 

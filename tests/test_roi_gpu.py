@@ -168,3 +168,57 @@ def test_cpu_device_is_refused():
     from multimodal_classification_b200._lib import VbError
     with pytest.raises(VbError):
         ResNet152ROIExtractor(device="cpu", weights=None)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json configs[2]
+GA = np.load(os.path.join(os.path.dirname(__file__), "golden", "roi_stage_448_align.npz"))
+
+
+@pytest.fixture(scope="module")
+def extractor_448_align():
+    from multimodal_classification_b200.resnet152_roi import ResNet152ROIExtractor
+    from oracle import roi_oracle as ro
+    ext = ResNet152ROIExtractor(device="cuda", weights=None, roi_size=7, image_size=448, pool_mode="roi_align")
+    ext.backbone.load_state_dict(ro.seeded_backbone_state(0), strict=True)
+    return ext
+
+
+def test_extract_features_448_roi_align_vs_reference(extractor_448_align):
+    """The whole stage at the BASELINE shape (3x448x448, RoIAlign 7x7, 36 boxes) against the reference extractor class run
+    with that transform / pooling op (oracle/make_golden_roi_align.py): boxes bit-equal, features at the bf16 bar."""
+    from PIL import Image
+    for i in range(2):
+        feats, spatial = extractor_448_align.extract_features(Image.fromarray(GA["images_u8"][i]))
+        assert feats.shape == (36, 2048) and feats.dtype == torch.float32
+        assert np.array_equal(spatial.cpu().numpy(), GA["spatial"][i])
+        ref, got = GA["features"][i], feats.cpu().numpy()
+        rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        mx = np.abs(got - ref).max() / np.abs(ref).max()
+        print(f"448/RoIAlign-7 picture {i}: rel-L2 {rel:.4f}  max-rel {mx:.4f}")
+        assert rel <= 2e-2 and mx <= 2e-2, (rel, mx)
+
+
+def test_roi_stage_feeds_the_encoder(extractor_448_align):
+    """configs[2] end to end, as pipelines/model_training/nodes.py:129-148, 195-202 chains it: pictures -> RoI stage -> ViLBERT
+    forward.  Both halves on the B200, compared with the reference classes chained the same way on the CPU in fp32."""
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    from oracle import vilbert_oracle as vo
+    cfg = vo.tiny_config()
+    cfg["v_feature_size"] = 2048
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(vo.seeded_state_dict(cfg), strict=True)
+    model = model.cuda().eval()
+    imgs = torch.from_numpy(GA["images_u8"]).permute(0, 3, 1, 2)
+    feats, spatial = extractor_448_align.forward(imgs)                  # [2, 36, 2048], [2, 36, 5] on the GPU
+    ids = torch.from_numpy(GA["chain_input_ids"]).cuda()
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=torch.from_numpy(GA["chain_attention_mask"]).cuda(),
+                    token_type_ids=torch.zeros_like(ids), visual_features=feats,
+                    visual_attention_mask=torch.ones(2, 36, dtype=torch.int64, device="cuda"), spatial_locations=spatial,
+                    labels=torch.from_numpy(GA["chain_labels"]).cuda())
+    ref = GA["chain_logits"]
+    err = np.abs(out["logits"].float().cpu().numpy() - ref).max()
+    # random-init logits of the tiny encoder are ~0.2: the bar is 2e-2 of max |logit| with the absolute floor the kernel tests
+    # use, and the loss bar of the fixtures
+    assert err <= 2e-2 * np.abs(ref).max() + 1e-3, (err, ref)
+    assert abs(out["loss"].item() - float(GA["chain_loss"])) <= 1e-3
