@@ -49,9 +49,9 @@ constexpr int GEMM_BOX_BF16 = 32 * GEMM_CHUNK * 2;   // 32 rows x 64 B, 64B-swiz
 constexpr int GEMM_BOX_F32 = 32 * GEMM_CHUNK * 4;    // 32 rows x 128 B, 128B-swizzled
 constexpr int GEMM_NBARS = 2 * GEMM_MAX_STAGES + 2 * GEMM_ACC_STAGES;
 #ifdef VB_GEMM_TRACE
-constexpr int GEMM_SMEM_SLACK = 512;   // static shared memory: barriers + the trace buffer
+constexpr int GEMM_SMEM_SLACK = 768;   // static shared memory: barriers + the trace buffer
 #else
-constexpr int GEMM_SMEM_SLACK = 256;   // static shared memory: barriers + TMEM base slot
+constexpr int GEMM_SMEM_SLACK = 512;   // static shared memory: barriers + TMEM base slot
 #endif
 // Tiles up to 128 columns wide use a compact configuration (<= 112 KB smem, <= 102 registers, <= 256 TMEM columns) so that
 // TWO CTAs (of different kernels: the text / visual / weight-gradient streams) can share an SM and overlap each other's
@@ -59,13 +59,15 @@ constexpr int GEMM_SMEM_SLACK = 256;   // static shared memory: barriers + TMEM 
 __host__ __device__ constexpr int gemm_smem_limit(int occ) { return (occ == 2 ? 112 * 1024 : 227 * 1024) - GEMM_SMEM_SLACK; }
 
 // shared-memory carve-up (offsets from the 1024-byte aligned base), the same arithmetic on host and device
-struct GemmSmem { uint32_t b, out, x, bias, scale, total; };
-__host__ __device__ inline GemmSmem gemm_smem(int stages, int bnl, int bn, bool f32, bool preact, bool has_scale) {
+struct GemmSmem { uint32_t b, out, x, aux, bias, scale, total; };
+// nbuf = staging boxes per epilogue warp (2: a chunk is staged while the previous one is still being read by its TMA store)
+__host__ __device__ inline GemmSmem gemm_smem(int stages, int bnl, int bn, bool f32, bool preact, bool has_scale, bool has_aux, int nbuf) {
   GemmSmem s;
   s.b = static_cast<uint32_t>(stages) * GEMM_A_BYTES;
   s.out = s.b + static_cast<uint32_t>(stages * bnl) * 128u;
-  s.x = s.out + GEMM_EPI_WARPS * (f32 ? GEMM_BOX_F32 : GEMM_BOX_BF16);
-  s.bias = s.x + (preact ? GEMM_EPI_WARPS * GEMM_BOX_BF16 : 0);
+  s.x = s.out + GEMM_EPI_WARPS * nbuf * (f32 ? GEMM_BOX_F32 : GEMM_BOX_BF16);
+  s.aux = s.x + (preact ? GEMM_EPI_WARPS * nbuf * GEMM_BOX_BF16 : 0);
+  s.bias = s.aux + (has_aux ? GEMM_EPI_WARPS * 2 * GEMM_BOX_BF16 : 0);      // aux boxes are always double-buffered
   const uint32_t strip = static_cast<uint32_t>((bn / GEMM_CHUNK + 1) / 2) * GEMM_CHUNK * 4u;   // floats of one warp's chunks
   s.scale = s.bias + GEMM_EPI_WARPS * strip;
   s.total = s.scale + (has_scale ? GEMM_EPI_WARPS * strip : 0u);
@@ -83,6 +85,9 @@ struct GemmKernelParams {
   int splits, kb_per_split;
   int m_tiles, n_tiles;
   int stages;       // depth of the operand ring
+  int nbuf;         // staging boxes per epilogue warp (1 | 2)
+  int a_3d, b_3d;   // the MN-major operand is fetched through a 3-D tensor map (64 | k | piece): one TMA instruction per tile
+  int pdl_late;     // trigger the dependent launch when the producer is done instead of at kernel entry
   int tmem_cols;
   int debug_mode;   // profiling only (VB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads; results are garbage
   uint32_t magic_m, magic_mn;   // fast_div multipliers for m_tiles and m_tiles * n_tiles
@@ -118,6 +123,12 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -161,6 +172,23 @@ __device__ __forceinline__ void tma_load_2d_warp(uint32_t dst, const CUtensorMap
                " [%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
                : "memory");
 }
+// MN-major operand tiles are made of 64-wide pieces (one 128-byte swizzle row per k); through a 3-D view of the matrix
+// (64 | k | piece) ONE instruction fetches all pieces of a tile, so that the producer issues two TMA instructions per k-block
+// whatever the layout.  Kept as an experiment (VB_GEMM_3D=1): on B200 it measured slower than one 2-D load per piece.
+__device__ __forceinline__ void tma_load_3d_pair_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%3, %4, %5}], [%2], %6;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+               "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%3, %4, %5}], [%2], %6;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+               "l"(policy)
+               : "memory");
+}
 // every lane polls (same barrier, same answer: no divergence), so the code after the wait is still warp-uniform
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
@@ -201,7 +229,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKernelParams& p, int 
 // call site (the chunk is unrolled).
 template <int EPI>
 __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const uint32_t* r /* 8 accumulator words */, int g,
-                                               uint32_t s_bias, uint32_t s_scale, const uint4& aux, uint32_t xrow, uint32_t orow,
+                                               uint32_t s_bias, uint32_t s_scale, uint32_t arow, uint32_t xrow, uint32_t orow,
                                                uint32_t swz64, uint32_t swz128) {
   float v[8];
 #pragma unroll
@@ -220,6 +248,8 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
     sts_u4(xrow + ((static_cast<uint32_t>(g) ^ swz64) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   if (EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || (EPI == EPI_GENERIC && p.aux_mode != VB_AUX_NONE)) {
+    // my row of the warp's aux box (TMA-loaded, 64-byte rows, 64B swizzle): piece g
+    const uint4 aux = lds_u4(arow + ((static_cast<uint32_t>(g) ^ swz64) << 4));
     const float2 a0 = unpack_bf16x2(aux.x), a1 = unpack_bf16x2(aux.y), a2 = unpack_bf16x2(aux.z), a3 = unpack_bf16x2(aux.w);
     const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
     if (EPI == EPI_AUX_ADD || (EPI == EPI_GENERIC && p.aux_mode == VB_AUX_ADD)) {
@@ -227,12 +257,17 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
       for (int i = 0; i < 8; ++i) v[i] += av[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= gelu_fast_grad(av[i]);
+      for (int i = 0; i < 8; i += 2) {
+        float g0, g1;
+        gelu_fast_grad2(av[i], av[i + 1], g0, g1);
+        v[i] *= g0;
+        v[i + 1] *= g1;
+      }
     }
   }
   if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.act == VB_ACT_GELU)) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+    for (int i = 0; i < 8; i += 2) gelu_fast2(v[i], v[i + 1]);
   } else if (EPI == EPI_GENERIC && p.act == VB_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
@@ -257,7 +292,8 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
 template <bool A_MN, bool B_MN, int CG, int NP>
 __device__ __forceinline__ void issue_kblock(const CUtensorMap* tma_a, const CUtensorMap* tma_b, uint32_t sa, uint32_t sb,
                                              uint32_t full_bar, uint32_t bar_leader, int bnl, int k0, int m0, int n0,
-                                             uint32_t prank, uint32_t pair, uint16_t a_mask, unsigned long long b_policy) {
+                                             uint32_t prank, uint32_t pair, uint16_t a_mask, unsigned long long b_policy, bool a3d,
+                                             bool b3d) {
   const int b_bytes = bnl * GEMM_BK * 2;
   if constexpr (CG == 2) {
     // both CTAs' bytes are counted on the leader's barrier; a peer load that lands before the leader's expect_tx only
@@ -271,26 +307,42 @@ __device__ __forceinline__ void issue_kblock(const CUtensorMap* tma_a, const CUt
       if constexpr (A_MN) tma_load_2d_pair_mc_warp(sa + pair * (GEMM_BK * 128), tma_a, bar_leader, m0 + static_cast<int>(pair) * 64, k0, a_mask);
       else                tma_load_2d_pair_mc_warp(sa + pair * (64 * 128), tma_a, bar_leader, k0, m0 + static_cast<int>(pair) * 64, a_mask);
     } else if constexpr (A_MN) {
+      if (a3d) {
+        tma_load_3d_pair_warp(sa, tma_a, bar_leader, 0, k0, m0 >> 6, L2_EVICT_NORMAL);
+      } else {
 #pragma unroll
-      for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair_warp(sa + j * (GEMM_BK * 128), tma_a, bar_leader, m0 + j * 64, k0, L2_EVICT_NORMAL);
+        for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair_warp(sa + j * (GEMM_BK * 128), tma_a, bar_leader, m0 + j * 64, k0, L2_EVICT_NORMAL);
+      }
     } else {
       tma_load_2d_pair_warp(sa, tma_a, bar_leader, k0, m0, L2_EVICT_NORMAL);
     }
     if constexpr (B_MN) {
-      for (int j = 0; j < bnl / 64; ++j) tma_load_2d_pair_warp(sb + j * (GEMM_BK * 128), tma_b, bar_leader, n0 + j * 64, k0, b_policy);
+      if (b3d) {
+        tma_load_3d_pair_warp(sb, tma_b, bar_leader, 0, k0, n0 >> 6, b_policy);
+      } else {
+        for (int j = 0; j < bnl / 64; ++j) tma_load_2d_pair_warp(sb + j * (GEMM_BK * 128), tma_b, bar_leader, n0 + j * 64, k0, b_policy);
+      }
     } else {
       tma_load_2d_pair_warp(sb, tma_b, bar_leader, k0, n0, b_policy);
     }
   } else {
     mbar_arrive_expect_tx_warp(full_bar, static_cast<uint32_t>(GEMM_A_BYTES + b_bytes));
     if constexpr (A_MN) {
+      if (a3d) {
+        tma_load_3d_warp(sa, tma_a, full_bar, 0, k0, m0 >> 6, L2_EVICT_NORMAL);
+      } else {
 #pragma unroll
-      for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_warp(sa + j * (GEMM_BK * 128), tma_a, full_bar, m0 + j * 64, k0, L2_EVICT_NORMAL);
+        for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_warp(sa + j * (GEMM_BK * 128), tma_a, full_bar, m0 + j * 64, k0, L2_EVICT_NORMAL);
+      }
     } else {
       tma_load_2d_warp(sa, tma_a, full_bar, k0, m0, L2_EVICT_NORMAL);
     }
     if constexpr (B_MN) {
-      for (int j = 0; j < bnl / 64; ++j) tma_load_2d_warp(sb + j * (GEMM_BK * 128), tma_b, full_bar, n0 + j * 64, k0, b_policy);
+      if (b3d) {
+        tma_load_3d_warp(sb, tma_b, full_bar, 0, k0, n0 >> 6, b_policy);
+      } else {
+        for (int j = 0; j < bnl / 64; ++j) tma_load_2d_warp(sb + j * (GEMM_BK * 128), tma_b, full_bar, n0 + j * 64, k0, b_policy);
+      }
     } else {
       tma_load_2d_warp(sb, tma_b, full_bar, k0, n0, b_policy);
     }
@@ -301,17 +353,18 @@ template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, OCC)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_x,
-                 const GemmKernelParams p_const) {
+                 const __grid_constant__ CUtensorMap tma_aux, const GemmKernelParams p_const) {
   constexpr int CS = CG * NP;                            // CTAs per cluster: NP pairs, side by side along N, sharing A
   static_assert(CG == 2 || NP == 1, "multicast clusters are built from CTA pairs");
   // barriers live in STATIC shared memory: their addresses are link-time constants, so warp 0 can initialise them with its very
   // first instructions -- before a single kernel parameter has been read -- and the cluster barrier that publishes them
   // completes that much earlier
   __shared__ __align__(8) uint64_t bars[GEMM_NBARS];
+  __shared__ __align__(8) uint64_t aux_bars[GEMM_EPI_WARPS * 2];     // one per (epilogue warp, aux box)
   __shared__ uint32_t tmem_base_slot[2];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) trace_stamp(0);
+  if (threadIdx.x == 0) { trace_stamp(0); tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b); }
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + GEMM_MAX_STAGES;
   uint64_t* tmem_full_bar = bars + 2 * GEMM_MAX_STAGES;
@@ -328,6 +381,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const bool is_tmem_empty = lane >= 2 * GEMM_MAX_STAGES + GEMM_ACC_STAGES;
     const bool is_empty = lane >= GEMM_MAX_STAGES && lane < 2 * GEMM_MAX_STAGES;
     if (lane < GEMM_NBARS) mbar_init(&bars[lane], is_tmem_empty ? GEMM_EPI_WARPS * CG : (is_empty ? NP : 1));
+    if (lane < GEMM_EPI_WARPS * 2) mbar_init(&aux_bars[lane], 1);
     __syncwarp();
     if (lane == 0) {
       fence_mbar_init();
@@ -336,16 +390,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __syncwarp();
   }
   if constexpr (CS > 1) cluster_arrive_relaxed();
-  // PDL: the next kernel of the stream may begin its own prologue; it blocks in griddepcontrol.wait until this grid is done
-  griddep_launch();
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tma_a); tma_prefetch_desc(&tma_b); }
   if (warp == 2 && lane == 0) tma_prefetch_desc(&tma_d);
 #ifdef VB_GEMM_TRACE
   if (threadIdx.x == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); s_trace[22] = static_cast<long long>(g); }
 #endif
 
   GemmKernelParams p = p_const;
-  pin(p.bn); pin(p.stages); pin(p.d_is_f32); pin(p.has_preact);
+  pin(p.bn); pin(p.stages); pin(p.d_is_f32); pin(p.has_preact); pin(p.nbuf); pin(p.pdl_late); pin(p.a_3d); pin(p.b_3d);
+  // PDL: the next kernel of the stream may begin its own prologue; it blocks in griddepcontrol.wait until this grid is done.
+  // (pdl_late: the producer triggers it after its last load instead -- a dependent that has waited long in
+  // griddepcontrol.wait wakes up late.)
+  if (!p.pdl_late) griddep_launch();
   pin(p.scale); pin(p.bias); pin(p.aux); pin(p.ld_aux); pin(p.m); pin(p.n); pin(p.k);
   pin(p.reduce_add); pin(p.act); pin(p.aux_mode);
   pin(p.splits); pin(p.kb_per_split); pin(p.m_tiles); pin(p.n_tiles); pin(p.tmem_cols);
@@ -358,7 +413,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const GemmSmem L = gemm_smem(STAGES, BNL, BN, p.d_is_f32 != 0, p.has_preact != 0, p.scale != nullptr);
+  const GemmSmem L = gemm_smem(STAGES, BNL, BN, p.d_is_f32 != 0, p.has_preact != 0, p.scale != nullptr, p.aux_mode != VB_AUX_NONE, p.nbuf);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + L.b;
 
@@ -405,12 +460,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         issue_kblock<A_MN, B_MN, CG, NP>(&tma_a, &tma_b, sa0 + static_cast<uint32_t>(stage * GEMM_A_BYTES),
                                          sb0 + static_cast<uint32_t>(stage * B_BYTES), full0 + static_cast<uint32_t>(stage) * 8u,
                                          full_leader + static_cast<uint32_t>(stage) * 8u, BNL, kb * GEMM_BK, m0, n0, prank, pair,
-                                         a_mask, b_policy);
+                                         a_mask, b_policy, p.a_3d != 0, p.b_3d != 0);
         if (lane == 0 && tile == first_tile && kb == kb0) trace_stamp(3);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
     if (lane == 0) trace_stamp(4);
+    if (p.pdl_late) griddep_launch();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ TMEM owner + MMA issuer (the leader CTA of every pair)
     if constexpr (CG == 2) {
@@ -493,13 +549,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const uint32_t strip = static_cast<uint32_t>((BN / GEMM_CHUNK + 1) / 2) * GEMM_CHUNK * 4u;
     const uint32_t sa_bias = smem_u32(smem + L.bias) + static_cast<uint32_t>(ewarp) * strip;
     const uint32_t sa_scale = p.scale != nullptr ? smem_u32(smem + L.scale) + static_cast<uint32_t>(ewarp) * strip : 0u;
-    uint8_t* box_out = smem + L.out + ewarp * (p.d_is_f32 ? GEMM_BOX_F32 : GEMM_BOX_BF16);
-    uint8_t* box_x = smem + L.x + ewarp * GEMM_BOX_BF16;
-    const uint32_t orow = smem_u32(box_out) + static_cast<uint32_t>(lane) * (p.d_is_f32 ? 128u : 64u);
-    const uint32_t xrow = smem_u32(box_x) + static_cast<uint32_t>(lane) * 64u;
+    const uint32_t out_box_bytes = p.d_is_f32 ? GEMM_BOX_F32 : GEMM_BOX_BF16;
+    // my staging boxes (nbuf of each kind, used alternately) and my two aux boxes
+    const uint32_t box_out0 = smem_u32(smem + L.out) + static_cast<uint32_t>(ewarp * p.nbuf) * out_box_bytes;
+    const uint32_t box_x0 = smem_u32(smem + L.x) + static_cast<uint32_t>(ewarp * p.nbuf) * GEMM_BOX_BF16;
+    const uint32_t box_aux0 = smem_u32(smem + L.aux) + static_cast<uint32_t>(ewarp * 2) * GEMM_BOX_BF16;
+    const uint32_t aux_bar0 = smem_u32(&aux_bars[ewarp * 2]);
+    const uint32_t row_out = static_cast<uint32_t>(lane) * (p.d_is_f32 ? 128u : 64u), row_bf16 = static_cast<uint32_t>(lane) * 64u;
+    uint32_t chunk_ctr = 0;       // chunks this warp has processed: selects the staging / aux box and the aux barrier parity
     const int nch = BN / GEMM_CHUNK;
-    const int n_oct = ((nch - half + 1) / 2) * 4;      // octets (8 columns) of my chunks per tile
-    if (p.has_preact && lane == 0 && ewarp == 1) tma_prefetch_desc(&tma_x);
+    if (lane == 0 && ewarp == 1) { if (p.has_preact) tma_prefetch_desc(&tma_x); if (has_aux) tma_prefetch_desc(&tma_aux); }
     tmem_slot_barrier();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot[0];
@@ -512,9 +571,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const TileCoord tc = decode_tile(p, tile);
       const int m0 = tc.m_idx * (GEMM_BM * CG) + static_cast<int>(prank) * GEMM_BM;
       const int n0 = (tc.n_idx * NP + static_cast<int>(pair)) * BN;
-      const int grow = m0 + row;
       const int r0 = m0 + quarter * 32;
-      const __nv_bfloat16* aux_row = (has_aux && grow < p.m) ? p.aux + static_cast<long long>(grow) * p.ld_aux : nullptr;
       // bias / scale of my chunks -> my strip (the previous tile's reads of the strip are complete: same warp, program order)
       __syncwarp();
       for (int j = 0, c = half; c < nch; ++j, c += 2) {
@@ -527,31 +584,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quarter * 32) << 16);
       // One 32-column chunk per iteration: the accumulator words arrive with ONE tcgen05.ld (a TMEM load has ~300 cycles of
       // latency whatever its width: 8-column loads in a rolled loop were 2x slower), the chunk is processed by straight-line
-      // code specialised at compile time, and the NEXT chunk's TMEM load and aux reads are issued before the current chunk is
-      // staged and stored.  Iteration -1 of the CTA's first tile is a dry run on zeros while the main loop is still computing:
-      // it pulls the epilogue code into the instruction cache (nothing is stored).
+      // code specialised at compile time, and everything the NEXT chunk needs is requested before the current one is processed:
+      // its TMEM load (second register buffer) and its aux box (TMA into the warp's other aux box).  Staging boxes alternate, so
+      // a chunk is staged while the previous store is still reading its box.  Iteration -1 of the CTA's first tile is a dry run on
+      // zeros while the main loop is still computing: it pulls the epilogue code into the instruction cache (nothing is stored).
       constexpr bool HAS_AUX = EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_GENERIC;
+      const bool use_aux = HAS_AUX && has_aux;
       const int my_chunks = (nch - half + 1) / 2;
-      uint32_t r[32];
-      uint4 a_cur[4], a_nxt[4];
+      uint32_t r[32], rn[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) r[i] = 0u;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a_cur[i] = make_uint4(0u, 0u, 0u, 0u); a_nxt[i] = make_uint4(0u, 0u, 0u, 0u); }
+      for (int i = 0; i < 32; ++i) { r[i] = 0u; rn[i] = 0u; }
       const bool warm = tile == first_tile;
 #pragma unroll 1
       for (int j = warm ? -1 : 0; j < my_chunks; ++j) {
         const bool live = j >= 0;
         const int jj = live ? j : 0;
         const int c = half + 2 * jj;
+        const uint32_t ab = chunk_ctr & 1u;                          // aux box / barrier of this chunk
+        const uint32_t sbuf = p.nbuf == 2 ? (chunk_ctr & 1u) : 0u;   // staging box of this chunk
         if (j == 0) {
-          // the accumulator of this tile: first aux reads are already in flight when the wait returns
-          if (HAS_AUX && has_aux) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = n0 + c * GEMM_CHUNK + 8 * q;
-              a_cur[q] = (aux_row != nullptr && col < p.n) ? ldg_nc_u4(aux_row + col) : make_uint4(0u, 0u, 0u, 0u);
-            }
+          // this tile's first aux box is requested before the accumulator wait (its latency hides behind the main loop)
+          if (use_aux && lane == 0) {
+            mbar_arrive_expect_tx(&aux_bars[ewarp * 2 + ab], GEMM_BOX_BF16);
+            tma_load_2d(smem + L.aux + (ewarp * 2 + ab) * GEMM_BOX_BF16, &tma_aux, &aux_bars[ewarp * 2 + ab], n0 + c * GEMM_CHUNK, r0);
           }
           mbar_wait(&tmem_full_bar[acc], acc_phase);
           tc_fence_after();
@@ -560,16 +615,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c * GEMM_CHUNK), r);
         }
         if (live) {
-          if (HAS_AUX && has_aux && j + 1 < my_chunks) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = n0 + (c + 2) * GEMM_CHUNK + 8 * q;
-              a_nxt[q] = (aux_row != nullptr && col < p.n) ? ldg_nc_u4(aux_row + col) : make_uint4(0u, 0u, 0u, 0u);
-            }
+          if (use_aux && j + 1 < my_chunks && lane == 0) {
+            // the other aux box was last read two chunks ago (same warp, program order)
+            mbar_arrive_expect_tx(&aux_bars[ewarp * 2 + (ab ^ 1u)], GEMM_BOX_BF16);
+            tma_load_2d(smem + L.aux + (ewarp * 2 + (ab ^ 1u)) * GEMM_BOX_BF16, &tma_aux, &aux_bars[ewarp * 2 + (ab ^ 1u)],
+                        n0 + (c + 2) * GEMM_CHUNK, r0);
           }
-          tmem_ld_wait();
+          tmem_ld_wait();                     // covers the load issued one iteration ago (into rn; into r for j == 0)
           if (tracer && j == 0) trace_stamp(12);
-          if (j + 1 == my_chunks) {
+          if (j > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = rn[i];
+          }
+          if (j + 1 < my_chunks) {
+            tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * GEMM_CHUNK), rn);     // arrives while this chunk is processed
+          } else {
             // my share of the accumulator stage is in registers: hand the stage back to the MMA warp (of the leader) right away
             tc_fence_before();
             __syncwarp();
@@ -578,33 +638,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               else                   mbar_arrive(&tmem_empty_bar[acc]);
             }
           }
-          if (lane == 0) tma_store_wait_read();   // my staging box(es) of the previous chunk have been read by the TMA engine
+          // my staging box: with two boxes the store issued two chunks ago must have been read, with one the previous store
+          if (lane == 0) { if (p.nbuf == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+          if (use_aux) mbar_wait_addr(aux_bar0 + ab * 8u, (chunk_ctr >> 1) & 1u);
           __syncwarp();
         }
         const uint32_t sb = sa_bias + static_cast<uint32_t>(jj * GEMM_CHUNK) * 4u;
         const uint32_t ss = sa_scale != 0u ? sa_scale + static_cast<uint32_t>(jj * GEMM_CHUNK) * 4u : 0u;
+        const uint32_t orow = box_out0 + sbuf * out_box_bytes + row_out;
+        const uint32_t xrow = box_x0 + sbuf * GEMM_BOX_BF16 + row_bf16;
+        const uint32_t arow = box_aux0 + ab * GEMM_BOX_BF16 + row_bf16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) epilogue_octet<EPI>(p, &r[8 * g], g, sb, ss, a_cur[g], xrow, orow, swz64, swz128);
-        if (live && j + 1 < my_chunks) tmem_ld_32x32(taddr + static_cast<uint32_t>((c + 2) * GEMM_CHUNK), r);   // r is free again
+        for (int g = 0; g < 4; ++g) epilogue_octet<EPI>(p, &r[8 * g], g, sb, ss, arow, xrow, orow, swz64, swz128);
         if (tracer && live && j == 0) trace_stamp(13);
         fence_proxy_async_smem();           // make the staged box visible to the TMA engine
         __syncwarp();
         const int c0 = n0 + c * GEMM_CHUNK;
-        if (live && lane == 0 && c0 < p.n && r0 < p.m) {
-          if (EPI == EPI_F32 || (EPI == EPI_GENERIC && p.d_is_f32)) {
-            if (p.reduce_add) tma_reduce_add_2d_hint(&tma_d, box_out, c0, r0, p.d_policy ? p.d_policy : L2_EVICT_NORMAL);
-            else              tma_store_2d_hint(&tma_d, box_out, c0, r0, p.d_policy ? p.d_policy : L2_EVICT_NORMAL);
-          } else {
-            tma_store_2d(&tma_d, box_out, c0, r0);
-            if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact)) tma_store_2d(&tma_x, box_x, c0, r0);
+        if (live && lane == 0) {
+          if (c0 < p.n && r0 < p.m) {
+            if (EPI == EPI_F32 || (EPI == EPI_GENERIC && p.d_is_f32)) {
+              if (p.reduce_add) tma_reduce_add_2d_hint(&tma_d, smem + L.out + (ewarp * p.nbuf + sbuf) * GEMM_BOX_F32, c0, r0, p.d_policy ? p.d_policy : L2_EVICT_NORMAL);
+              else              tma_store_2d_hint(&tma_d, smem + L.out + (ewarp * p.nbuf + sbuf) * GEMM_BOX_F32, c0, r0, p.d_policy ? p.d_policy : L2_EVICT_NORMAL);
+            } else {
+              tma_store_2d(&tma_d, smem + L.out + (ewarp * p.nbuf + sbuf) * GEMM_BOX_BF16, c0, r0);
+              if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact))
+                tma_store_2d(&tma_x, smem + L.x + (ewarp * p.nbuf + sbuf) * GEMM_BOX_BF16, c0, r0);
+            }
           }
-          tma_store_commit();
+          tma_store_commit();               // one (possibly empty) group per chunk: wait_group.read 1 counts chunks
           if (tracer && j == 0) trace_stamp(16);
         }
-        if (HAS_AUX && live) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) a_cur[q] = a_nxt[q];
-        }
+        if (live) ++chunk_ctr;
       }
       if (++acc == GEMM_ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
@@ -655,15 +719,25 @@ static int num_sms() {
 }
 
 // experiment knobs: read once from the environment, overridable at run time through vb_gemm_set_knob (tools/gemm_mainloop.py)
-struct GemmKnobs { int occ1, max_bn, np, cg, debug_mode, stages, no_l2_hints; };
+struct GemmKnobs { int occ1, max_bn, np, cg, debug_mode, stages, no_l2_hints, compact, pdl_late; };
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 static GemmKnobs& knobs() {
   static GemmKnobs k = {env_int("VB_GEMM_OCC1", 0), env_int("VB_GEMM_MAX_BN", 256), env_int("VB_GEMM_NP", 0), env_int("VB_GEMM_CG", 0),
-                        env_int("VB_GEMM_DEBUG", 0), env_int("VB_GEMM_STAGES", 0), env_int("VB_GEMM_NO_L2_HINTS", 0)};
+                        env_int("VB_GEMM_DEBUG", 0), env_int("VB_GEMM_STAGES", 0), env_int("VB_GEMM_NO_L2_HINTS", 0),
+                        env_int("VB_GEMM_COMPACT", 0), env_int("VB_GEMM_PDL_LATE", 0)};
   return k;
 }
-static bool occ1_forced() { return knobs().occ1 != 0; }
-static int gemm_occupancy(int bn) { return (bn <= 128 && !occ1_forced()) ? 2 : 1; }
+// Residency target per SM.  VB_GEMM_COMPACT (knob "compact"): 0 = one CTA per SM for every GEMM (default: deep operand ring,
+// double-buffered epilogue, up to 200 registers), 1 = tiles up to 128 wide use the compact configuration (<= 112 KB, <= 96
+// registers) so that CTAs of two kernels can share an SM, 2 = compact for fp32 outputs (weight gradients) only, 3 = compact for
+// bf16 outputs only.
+static int gemm_occupancy(const vb_gemm_args& a, int bn) {
+  const int mode = knobs().occ1 ? 0 : knobs().compact;
+  if (bn > 128 || mode == 0) return 1;
+  if (mode == 2) return a.d_is_f32 ? 2 : 1;
+  if (mode == 3) return a.d_is_f32 ? 1 : 2;
+  return 2;
+}
 
 // Co-resident clusters of `cs` CTAs (one CTA per SM).  Clusters cannot straddle a GPC and the B200's GPCs do not all hold a
 // multiple of four SMs, so fewer than 148 / cs clusters of four fit; asked of the driver once per cluster size.
@@ -711,12 +785,15 @@ static int max_clusters(int cs, int occupancy) {
   return cached[cs][occupancy];
 }
 
-static int gemm_stages(int bn, int cg, bool f32, bool preact, bool has_scale) {
-  const int occ = gemm_occupancy(bn);
+static int gemm_nbuf(const vb_gemm_args& a, int bn) { return gemm_occupancy(a, bn) == 1 ? 2 : 1; }
+static int gemm_stages(const vb_gemm_args& a, int bn, int cg) {
+  const int occ = gemm_occupancy(a, bn);
   const int bnl = bn / cg;
-  const GemmSmem z = gemm_smem(0, bnl, bn, f32, preact, has_scale);
+  const GemmSmem z = gemm_smem(0, bnl, bn, a.d_is_f32 != 0, a.d_preact != nullptr, a.scale != nullptr, a.aux_mode != VB_AUX_NONE, gemm_nbuf(a, bn));
   int stages = (gemm_smem_limit(occ) - 1024 /*alignment slack*/ - static_cast<int>(z.total)) / (GEMM_A_BYTES + bnl * 128);
-  if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+  // measured (tools/gemm_mainloop.py): the main loop runs at the same rate with 3 and with 8 stages; 6 leave room for the
+  // double-buffered epilogue and keep the footprint of a CTA (and its TMA traffic in flight) moderate
+  if (stages > 6) stages = 6;
   return stages;
 }
 
@@ -724,14 +801,25 @@ template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI>
 static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t stream) {
   constexpr int CS = CG * NP;
   const int bnl = bn / CG;
-  CUtensorMap map_a, map_b, map_d, map_x;
+  CUtensorMap map_a, map_b, map_d, map_x, map_aux;
   int rc;
   // K-major operand: global [rows, K] -> box {64 (k), rows_per_cta}; MN-major: global [K, rows] -> box {64 (mn), 64 (k)}
-  if (A_MN) rc = make_tensor_map_2d(&map_a, a.a, /*inner*/ a.m, /*outer*/ a.k, a.lda, 64, GEMM_BK);
-  else      rc = make_tensor_map_2d(&map_a, a.a, a.k, a.m, a.lda, GEMM_BK, GEMM_BM / NP);   // NP = 2: multicast halves
+  // An MN-major operand whose MN extent is a multiple of 64 is described as (64 | k | MN / 64): one box = every 64-wide piece
+  // of a tile (with a ragged last piece the flat 2-D description and one load per piece stay in use: a 3-D view would run
+  // over the row end instead of reading zeros).
+  // Opt-in (VB_GEMM_3D=1): measured SLOWER than one 2-D load per piece on B200 (weight gradients 1 031 -> 1 270 us per step,
+  // profiles/r02_gemm_experiments.md) -- the 3-D box with a 128-byte innermost extent is unpacked less efficiently by the TMA unit
+  // than the issue cost it saves.
+  static const bool use_3d = env_int("VB_GEMM_3D", 0) != 0;
+  const bool a_3d = A_MN && NP == 1 && a.m % 64 == 0 && use_3d;
+  const bool b_3d = B_MN && bnl > 64 && a.n % 64 == 0 && use_3d;
+  if (a_3d)      rc = make_tensor_map_3d(&map_a, a.a, 64, a.k, a.m / 64, a.lda, 64, 64, GEMM_BK, GEMM_BM / 64);
+  else if (A_MN) rc = make_tensor_map_2d(&map_a, a.a, /*inner*/ a.m, /*outer*/ a.k, a.lda, 64, GEMM_BK);
+  else           rc = make_tensor_map_2d(&map_a, a.a, a.k, a.m, a.lda, GEMM_BK, GEMM_BM / NP);   // NP = 2: multicast halves
   if (rc != VB_OK) return rc;
-  if (B_MN) rc = make_tensor_map_2d(&map_b, a.b, a.n, a.k, a.ldb, 64, GEMM_BK);
-  else      rc = make_tensor_map_2d(&map_b, a.b, a.k, a.n, a.ldb, GEMM_BK, bnl);
+  if (b_3d)      rc = make_tensor_map_3d(&map_b, a.b, 64, a.k, a.n / 64, a.ldb, 64, 64, GEMM_BK, bnl / 64);
+  else if (B_MN) rc = make_tensor_map_2d(&map_b, a.b, a.n, a.k, a.ldb, 64, GEMM_BK);
+  else           rc = make_tensor_map_2d(&map_b, a.b, a.k, a.n, a.ldb, GEMM_BK, bnl);
   if (rc != VB_OK) return rc;
   // epilogue boxes: 32 rows x 32 columns per warp (fp32: 128-byte rows, 128B swizzle; bf16: 64-byte rows, 64B swizzle)
   if (a.d_is_f32) rc = make_tensor_map_2d_f32(&map_d, a.d, a.n, a.m, a.ldd, GEMM_CHUNK, 32);
@@ -742,6 +830,12 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
     if (rc != VB_OK) return rc;
   } else {
     map_x = map_d;
+  }
+  if (a.aux_mode != VB_AUX_NONE) {
+    rc = make_tensor_map_2d_sw64(&map_aux, a.aux, a.n, a.m, a.ld_aux, GEMM_CHUNK, 32);
+    if (rc != VB_OK) return rc;
+  } else {
+    map_aux = map_d;
   }
 
   GemmKernelParams p;
@@ -767,7 +861,11 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
     p.magic_m = p.m_tiles == 1 ? 0u : static_cast<uint32_t>(((1ull << 32) + p.m_tiles - 1) / p.m_tiles);
     p.magic_mn = mn == 1 ? 0u : static_cast<uint32_t>(((1ull << 32) + mn - 1) / mn);
   }
-  int stages = gemm_stages(bn, CG, a.d_is_f32 != 0, p.has_preact != 0, a.scale != nullptr);
+  int stages = gemm_stages(a, bn, CG);
+  p.nbuf = gemm_nbuf(a, bn);
+  p.pdl_late = knobs().pdl_late;
+  p.a_3d = a_3d ? 1 : 0;
+  p.b_3d = b_3d ? 1 : 0;
   if (stages < 2) {
     vb_set_last_error("vb_gemm_bf16", "tile configuration does not fit shared memory");
     return VB_ERR_UNSUPPORTED;
@@ -782,7 +880,7 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   p.stages = stages;
   p.tmem_cols = 32;
   while (p.tmem_cols < GEMM_ACC_STAGES * bn) p.tmem_cols *= 2;
-  const GemmSmem L = gemm_smem(stages, bnl, bn, a.d_is_f32 != 0, p.has_preact != 0, a.scale != nullptr);
+  const GemmSmem L = gemm_smem(stages, bnl, bn, a.d_is_f32 != 0, p.has_preact != 0, a.scale != nullptr, a.aux_mode != VB_AUX_NONE, p.nbuf);
   const int smem_bytes = 1024 + static_cast<int>(L.total);
 
   static bool attr_set = false;   // one per instantiation
@@ -796,7 +894,7 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   if (a.max_ctas > 0 && a.max_ctas / CS < groups) groups = a.max_ctas / CS > 0 ? a.max_ctas / CS : 1;
   if (tiles < groups) groups = tiles;
   VB_CUDA_CHECK(launch_ex(kern, dim3(groups * CS), dim3(GEMM_THREADS), smem_bytes, stream, CS, /*pdl=*/true, map_a, map_b,
-                          map_d, map_x, p));
+                          map_d, map_x, map_aux, p));
   return VB_OK;
 }
 
@@ -808,7 +906,7 @@ struct TileChoice { int bn, cg, np, splits; };
 
 static double tile_cost(const vb_gemm_args& a, int bn, int cg, int np, int kb, double ctas, double waves, bool split) {
   const bool f32 = a.d_is_f32 != 0;
-  const int stages = gemm_stages(bn, cg, f32, a.d_preact != nullptr, a.scale != nullptr);
+  const int stages = gemm_stages(a, bn, cg);
   const double sms = ctas < num_sms() ? ctas : num_sms();
   const double share = ctas / sms;     // two small CTAs co-resident share the SM's ingest bandwidth and tensor pipe
   const double a_bytes = GEMM_BM * 128.0, b_bytes = (bn / cg) * 128.0;
@@ -853,7 +951,7 @@ static TileChoice pick_config(const vb_gemm_args& a) {
         for (int bi = 0; bi < 7; ++bi) {
           const int bn = bns[bi];
           if (!tile_legal(a, bn, cg)) continue;
-          int clusters = max_clusters(cg * np, gemm_occupancy(bn));
+          int clusters = max_clusters(cg * np, gemm_occupancy(a, bn));
           if (a.max_ctas > 0 && a.max_ctas / (cg * np) < clusters) clusters = a.max_ctas / (cg * np) > 0 ? a.max_ctas / (cg * np) : 1;
           if (pass == 0 && a.block_n != 0 && a.block_n != bn) continue;
           if (bn > 64 && a.n <= bn / 2 && pass == 0 && a.block_n == 0) continue;  // do not waste most of a tile
@@ -913,7 +1011,7 @@ static int dispatch_major(const vb_gemm_args& a, int bn, int splits, cudaStream_
 
 template <int CG, int NP>
 static int dispatch_occ(const vb_gemm_args& a, const TileChoice& c, cudaStream_t s) {
-  if (gemm_occupancy(c.bn) == 2) return dispatch_major<CG, NP, 2>(a, c.bn, c.splits, s);
+  if (gemm_occupancy(a, c.bn) == 2) return dispatch_major<CG, NP, 2>(a, c.bn, c.splits, s);
   return dispatch_major<CG, NP, 1>(a, c.bn, c.splits, s);
 }
 
@@ -943,7 +1041,8 @@ extern "C" int vb_gemm_set_knob(const char* name, int value) {
   using namespace vb;
   GemmKnobs& k = knobs();
   const struct { const char* n; int* v; } tab[] = {{"occ1", &k.occ1}, {"max_bn", &k.max_bn}, {"np", &k.np}, {"cg", &k.cg},
-                                                   {"debug_mode", &k.debug_mode}, {"stages", &k.stages}, {"no_l2_hints", &k.no_l2_hints}};
+                                                   {"debug_mode", &k.debug_mode}, {"stages", &k.stages}, {"no_l2_hints", &k.no_l2_hints},
+                                                   {"compact", &k.compact}, {"pdl_late", &k.pdl_late}};
   for (const auto& e : tab)
     if (strcmp(e.n, name) == 0) { *e.v = value; return VB_OK; }
   vb_set_last_error("vb_gemm_set_knob", "unknown knob");
@@ -989,7 +1088,7 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* args, void* stream) {
   if (verbose)
     fprintf(stderr, "vb_gemm %dx%dx%d a_mn=%d b_mn=%d f32=%d -> bn=%d cg=%d np=%d splits=%d stages=%d (clusters %d)\n", a.m, a.n, a.k,
             a.a_mn_major, a.b_mn_major, a.d_is_f32, c.bn, c.cg, c.np, c.splits,
-            gemm_stages(c.bn, c.cg, a.d_is_f32 != 0, a.d_preact != nullptr, a.scale != nullptr), max_clusters(c.cg * c.np, gemm_occupancy(c.bn)));
+            gemm_stages(a, c.bn, c.cg), max_clusters(c.cg * c.np, gemm_occupancy(a, c.bn)));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (c.cg == 1) return dispatch_occ<1, 1>(a, c, s);
   if (c.np == 2) return dispatch_occ<2, 2>(a, c, s);

@@ -375,7 +375,7 @@ class _Engine:
         # SM partitioning: weight-gradient GEMMs (side streams, off the critical path) are capped to a slice of the SMs so
         # that a dgrad-chain kernel never has to wait for a chip-wide weight-gradient grid to drain
         self.fp32_residual = os.environ.get("VB_BF16_RESIDUAL", "0") != "1"
-        self.wgrad_ctas = int(os.environ.get("VB_WGRAD_CTAS", "48"))     # measured: 0 -> 5.92 ms, 32 -> 5.86, 48 -> 5.83, 64 -> 5.89 per step
+        self.wgrad_ctas = int(os.environ.get("VB_WGRAD_CTAS", "74"))     # measured (round 2 kernels): 0 -> 4.93 ms, 32 -> 5.00, 48 -> 4.83, 74 -> 4.78, 100 -> 4.78 per step
         self._pl = None
         self.launches = 0
         # range-check verdict of the staging kernel: one int32 in mapped pinned host memory (see _raise_on_bad_indices)

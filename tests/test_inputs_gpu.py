@@ -26,7 +26,7 @@ def _cuda(b):
 def test_staging_is_one_launch_and_bit_exact():
     from multimodal_classification_b200 import _lib
     model, cfg = _model()
-    b = _cuda(vo.synthetic_batch(cfg, batch=4, seq=32, regions=16, seed=3))
+    b = _cuda(vo.synthetic_batch(cfg, batch=4, seq=32, regions=16, seed=3, with_visual_mask=True))
     with torch.no_grad():
         model(**b)                                   # eager warm-up
         model(**b)                                   # captures the forward graph
