@@ -372,8 +372,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eval-dropout-off", action="store_true", help="time with dropout off (parity configuration)")
+    ap.add_argument("--core-only", action="store_true", help="headline legs only (profiling runs): no stock-optimizer / ingest / RoI / inference legs")
+    ap.add_argument("--steps-only", action="store_true", help="warm-up + K resident steps and nothing else (the command ncu wraps for the launch list)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.core_only:
+        os.environ["VB_BENCH_SKIP_EXTRA"] = os.environ["VB_BENCH_SKIP_STOCK"] = os.environ["VB_BENCH_SKIP_INGEST"] = "1"
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -404,8 +408,20 @@ def main():
     if world > 1 and os.environ.get("VB_DDP_SKIP", "0") != "1":      # VB_DDP_SKIP: diagnostic only (replicas without exchange)
         if os.environ.get("VB_DDP_FLUSH_MB"):
             vb_ddp.FLUSH_BYTES = int(os.environ["VB_DDP_FLUSH_MB"]) << 20
-        grad_exchange = "fp32" if os.environ.get("VB_DDP_FP32", "0") == "1" else "bf16"
-        vb_ddp.attach(model, dist.group.WORLD, compress=None if grad_exchange == "fp32" else "bf16")
+        # gradient exchange of the scaling runs: bf16 through our own NVSwitch kernels (multimem reduce in the switch; the weight-
+        # gradient GEMMs write bf16 straight into the symmetric buffer).  VB_DDP_TRANSPORT=nccl: bucketed NCCL all-reduce of bf16
+        # casts; VB_DDP_FP32=1: fp32 over NCCL (numerically the single-GPU step).  A box without symmetric-memory support falls
+        # back to NCCL and says so in config.grad_exchange.
+        transport = os.environ.get("VB_DDP_TRANSPORT", "switch")
+        if os.environ.get("VB_DDP_FP32", "0") == "1":
+            grad_exchange = "fp32 (NCCL all-reduce)"
+            vb_ddp.attach(model, dist.group.WORLD, compress=None)
+        elif transport == "switch" and vb_ddp.switch_available(dist.group.WORLD, dev):
+            grad_exchange = "bf16 (own NVSwitch kernels: multimem.ld_reduce / multimem.st)"
+            vb_ddp.attach(model, dist.group.WORLD, compress="bf16", transport="switch")
+        else:
+            grad_exchange = "bf16 (NCCL all-reduce)" + (" [switch transport unavailable on this box]" if transport == "switch" else "")
+            vb_ddp.attach(model, dist.group.WORLD, compress="bf16")
     host = vo.synthetic_batch(cfg, batch=B, seq=T, regions=R, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
@@ -455,6 +471,12 @@ def main():
     launches = launches_direct // max(1, args.steps) + plan.fwd_launches + plan.bwd_launches   # kernels per step
     ms_per_step = ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+
+    if args.steps_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": args.steps,
+                              "warmup": args.warmup, "gpu_launches_per_step": int(launches), "note": "steps only (profiling run)"}), flush=True)
+        return
 
     # ---- end to end through the public API with host buffers: H2D of the batch and D2H of the loss inside the region
     def e2e_step():
@@ -507,7 +529,7 @@ def main():
     # ---- the same step fed by the feature-store loader: records decoded from an in-memory LMDB image
     #      by the producer thread, one pinned blob + one H2D + one unpack launch per batch, overlapped with the previous step
     ingest = None
-    if world == 1:
+    if world == 1 and os.environ.get("VB_BENCH_SKIP_INGEST", "0") != "1":
         try:
             ingest = time_ingest(torch, dev, step, timed, max(args.steps, 60))
         except Exception as e:      # the headline line must still print

@@ -89,6 +89,31 @@ int vb_gemm_set_knob(const char* name, int value);
 int vb_gemm_debug_occupancy(int smem_bytes, int* blocks_per_sm, int* clusters);
 
 /* ------------------------------------------------------------------------------------------------
+ * Gradient exchange over NVLink / NVSwitch (data-parallel training: the one exchange step of the path; the
+ * reference itself is single-GPU).  In-place mean all-reduce of the bf16 range [lo, hi) (elements, multiples of 8) of a
+ * symmetric buffer: three launches on `stream` (rank barrier, slice reduce + broadcast, rank barrier).
+ *   mc_base     multicast mapping of the buffer (NVLS: multimem.ld_reduce / multimem.st), or NULL
+ *   peer_bases  DEVICE array of `world` pointers to every rank's mapping of the buffer (used when mc_base is NULL)
+ *   flag_ptrs   DEVICE array of `world` pointers to every rank's flag pad (uint32, zero-initialised, flag_slots * world words)
+ *   ctas        CTAs of the reduce kernel (0 = default)
+ *   out_mc_base / out_peer_bases   optional SECOND symmetric buffer of fp32: when given, the mean of bf16 elements [lo, hi) is
+ *               broadcast as fp32 into elements [out_lo, out_lo + hi - lo) of it on every rank (the bf16 buffer is left as it
+ *               was); when both are NULL the result replaces the bf16 range in place.
+ * vb_rank_barrier is the hand-shake alone (slot in [0, flag_slots)). */
+typedef struct vb_exchange_args {
+  void* mc_base;
+  const void* peer_bases;
+  const void* flag_ptrs;
+  int32_t rank, world;
+  int32_t flag_slots;
+  int32_t ctas;
+  void* out_mc_base;
+  const void* out_peer_bases;
+} vb_exchange_args;
+int vb_allreduce_mean_bf16(const vb_exchange_args* args, int64_t lo, int64_t hi, int64_t out_lo, void* stream);
+int vb_rank_barrier(const vb_exchange_args* args, int32_t slot, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Row-wise bandwidth kernels (one warp per row, 16-byte accesses, fp32 math on bf16 storage).
  * Dropout masks are a pure function of (*seed, site, element index): forward and backward regenerate
  * them, nothing is stored.  `seed` is a DEVICE pointer so that a captured CUDA graph sees a new seed on

@@ -84,6 +84,12 @@ class StageSeg(C.Structure):
                 ("lo", C.c_int32), ("hi", C.c_int32), ("err_bit", C.c_int32)]
 
 
+class ExchangeArgs(C.Structure):
+    _fields_ = [("mc_base", C.c_void_p), ("peer_bases", C.c_void_p), ("flag_ptrs", C.c_void_p), ("rank", C.c_int32),
+                ("world", C.c_int32), ("flag_slots", C.c_int32), ("ctas", C.c_int32), ("out_mc_base", C.c_void_p),
+                ("out_peer_bases", C.c_void_p)]
+
+
 DT_F32, DT_I32, DT_I64, DT_BF16 = 0, 1, 2, 3
 STAGE_INDEX, STAGE_MASK, STAGE_FEAT, STAGE_COPY_F32 = 0, 1, 2, 3
 STAGE_ERR_ID, STAGE_ERR_TYPE, STAGE_ERR_LABEL = 1, 2, 4
@@ -128,6 +134,8 @@ def _declare(l: C.CDLL) -> None:
         "vb_seed_advance": [vp, vp],
         "vb_seed_advance_to": [vp, vp, vp],
         "vb_stage_batch": [C.POINTER(StageSeg), i32, vp, vp],
+        "vb_allreduce_mean_bf16": [C.POINTER(ExchangeArgs), i64, i64, i64, vp],
+        "vb_rank_barrier": [C.POINTER(ExchangeArgs), i32, vp],
         "vb_act_bwd_bf16": [vp, vp, vp, i64, i32, vp],
         "vb_loc_embed_fwd": [vp, vp, vp, vp, i32, i32, i32, vp],
         "vb_loc_embed_bwd": [vp, vp, vp, vp, i32, i32, i32, vp],

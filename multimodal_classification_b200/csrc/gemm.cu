@@ -1001,6 +1001,7 @@ static int dispatch_major(const vb_gemm_args& a, int bn, int splits, cudaStream_
       if (epi == EPI_AUX_GELUGRAD) return launch_gemm<false, true, CG, NP, OCC, EPI_AUX_GELUGRAD>(a, bn, splits, s);
     } else if (a.a_mn_major && a.b_mn_major) {
       if (epi == EPI_F32) return launch_gemm<true, true, CG, NP, OCC, EPI_F32>(a, bn, splits, s);
+      if (epi == EPI_BIAS) return launch_gemm<true, true, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);   // bf16 weight gradients (switch exchange)
     }
   }
   if (a.a_mn_major && a.b_mn_major) return launch_gemm<true, true, CG, NP, OCC, EPI_GENERIC>(a, bn, splits, s);

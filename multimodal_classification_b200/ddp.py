@@ -41,7 +41,90 @@ def all_reduce_mean(t: torch.Tensor, group) -> None:
         t.mul_(1.0 / dist.get_world_size(group))
 
 
-def attach(model, group=None, compress=None) -> None:
+class SwitchExchange:
+    """bf16 gradient exchange through NVSwitch by our own kernels (csrc/comm.cu) instead of NCCL: one symmetric bf16 buffer laid
+    out like the flat gradient buffer -- the weight-gradient GEMMs write into it directly -- whose ranges are mean-all-reduced in
+    place (multimem.ld_reduce / multimem.st when the fabric offers a multicast mapping, peer loads / stores otherwise).
+    torch.distributed._symmetric_memory allocates and maps the memory (plumbing only)."""
+    FLAG_SLOTS = 4
+
+    def __init__(self, numel: int, device, group, fp32_out: bool = False):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        n = (numel + 127) // 128 * 128
+        try:                                             # older torch: groups are enabled explicitly (a no-op / deprecated later)
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.buf = symm.empty(n, dtype=torch.bfloat16, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        # optional second symmetric buffer: the fp32 gradient buffer itself, so that the reduced values are broadcast widened
+        self.grad = self.grad_handle = None
+        if fp32_out:
+            self.grad = symm.empty(n, dtype=torch.float32, device=device)
+            self.grad.zero_()
+            self.grad_handle = symm.rendezvous(self.grad, group)
+        self.flags = symm.empty(self.FLAG_SLOTS * self.world, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.flag_handle = symm.rendezvous(self.flags, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                              # every rank's flags are zero before the first hand-shake
+        a = self.args = _lib.ExchangeArgs()
+        mc = int(self.handle.multicast_ptr or 0)         # 0 when the fabric / driver offers no multicast mapping
+        self.multicast = mc != 0
+        a.mc_base = mc if mc else None
+        a.peer_bases = int(self.handle.buffer_ptrs_dev)
+        a.flag_ptrs = int(self.flag_handle.buffer_ptrs_dev)
+        a.rank, a.world, a.flag_slots, a.ctas = self.rank, self.world, self.FLAG_SLOTS, int(__import__("os").environ.get("VB_DDP_CTAS", "0"))
+        if self.grad_handle is not None:
+            gmc = int(self.grad_handle.multicast_ptr or 0)
+            a.out_mc_base = gmc if (gmc and mc) else None
+            a.out_peer_bases = int(self.grad_handle.buffer_ptrs_dev)
+
+    def all_reduce_mean(self, lo: int, hi: int) -> None:
+        """Mean over ranks of buf[lo:hi] (on the current stream; lo / hi multiples of 8): written to grad[lo:hi] in fp32 on every
+        rank when the exchange owns the fp32 gradient buffer, else in place in bf16."""
+        import ctypes as C
+        from . import _lib
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().vb_allreduce_mean_bf16(C.byref(self.args), lo, hi, lo, stream), "vb_allreduce_mean_bf16")
+
+
+def switch_available(group=None, device=None) -> bool:
+    """Collective probe: can every rank of `group` build (and use) a SwitchExchange?  False on boxes without symmetric-memory /
+    peer-access support, so that callers can fall back to the NCCL transport."""
+    group = group if group is not None else dist.group.WORLD
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    ok = 1
+    try:
+        ex = SwitchExchange(1 << 16, device, group, fp32_out=True)
+        ex.buf.fill_(float(dist.get_rank(group) + 1))
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+        ex.all_reduce_mean(0, 1 << 16)
+        torch.cuda.synchronize(device)
+        n = dist.get_world_size(group)
+        ok = int(bool((ex.grad[:1 << 16] == (n + 1) / 2.0).all()))
+        ex2 = SwitchExchange(1 << 16, device, group)                # and the in-place bf16 form
+        ex2.buf.fill_(float(dist.get_rank(group) + 1))
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+        ex2.all_reduce_mean(0, 1 << 16)
+        torch.cuda.synchronize(device)
+        ok &= int(bool((ex2.buf[:1 << 16].float() == (n + 1) / 2.0).all()))
+    except Exception as e:      # noqa: BLE001 -- any failure means "not available here"
+        print(f"[ddp] switch transport unavailable: {e!r}"[:300], flush=True)
+        ok = 0
+    t = torch.tensor([ok], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return bool(t.item())
+
+
+def attach(model, group=None, compress=None, transport: str = "nccl") -> None:
     """Make `model` (multimodal_classification_b200.vilbert.ViLBERTForClassification) average its gradients over
     `group` inside every backward pass.  Parameters must already be identical on all ranks (same seed / same
     state_dict); call broadcast_parameters() otherwise.
@@ -49,11 +132,19 @@ def attach(model, group=None, compress=None) -> None:
     compress=None (default): the exchange is in fp32, numerically the single-GPU step on the global batch.
     compress="bf16" (opt-in): every bucket is narrowed to bf16 by a cast kernel, all-reduced (498 MB instead of 995 MB per
     step over NVLink) and widened back into the fp32 gradient buffer -- the usual bf16 gradient-compression trade (one extra
-    rounding of the averaged gradient, relative error <= 2^-8)."""
+    rounding of the averaged gradient, relative error <= 2^-8).
+    transport="switch" (with compress="bf16"): no NCCL and no narrowing pass -- the weight-gradient GEMMs write bf16 straight
+    into a symmetric buffer that our own NVSwitch kernels reduce in place (SwitchExchange); the result is widened into the fp32
+    gradient views once."""
     if compress not in (None, "bf16"):
         raise ValueError("compress must be None or 'bf16'")
+    if transport not in ("nccl", "switch"):
+        raise ValueError("transport must be 'nccl' or 'switch'")
+    if transport == "switch" and compress != "bf16":
+        raise ValueError("transport='switch' exchanges bf16 gradients: pass compress='bf16'")
     model._ddp_group = group if group is not None else dist.group.WORLD
     model._ddp_compress = compress
+    model._ddp_transport = transport
     model._engine = None
 
 

@@ -388,8 +388,19 @@ class _Engine:
         self.comm_group = getattr(model, "_ddp_group", None)   # data-parallel: see ddp.attach()
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if self.comm_group is not None else None   # as urgent as the chain: NCCL CTAs must get SM slots while GEMMs are running
         self.comm_compress = getattr(model, "_ddp_compress", None) if self.comm_group is not None else None
+        self.comm_switch = None
+        if self.comm_group is not None and getattr(model, "_ddp_transport", "nccl") == "switch":
+            from . import ddp
+            # VB_DDP_FP32_BCAST=1: the fp32 gradient buffer becomes a symmetric buffer too and the reduce kernel broadcasts the
+            # mean into it already widened.  Measured SLOWER at N = 2 (5.97 vs 5.55 ms/step): twice the bytes on the links,
+            # own copy included (multicast stores loop back through the switch); the default broadcasts bf16 in place and
+            # widens locally.
+            fp32_bcast = os.environ.get("VB_DDP_FP32_BCAST", "0") == "1"
+            self.comm_switch = ddp.SwitchExchange(self.flat.s_end, device, self.comm_group, fp32_out=fp32_bcast)
+            if fp32_bcast:
+                self.flat.grad = self.comm_switch.grad[:self.flat.s_end]
         self.comm_staging = (torch.empty(self.flat.s_end, dtype=torch.bfloat16, device=device)
-                             if self.comm_compress == "bf16" else None)
+                             if self.comm_compress == "bf16" and self.comm_switch is None else None)
         self._pending, self._pending_streams = [], set()
         self._site = 0
         f = self.flat
@@ -422,13 +433,21 @@ class _Engine:
         with torch.cuda.stream(side if side is not None else cur):
             # fp32 accumulate into the (pre-zeroed) flat gradient buffer: lets the GEMM split the long token dimension
             # over more CTAs (TMA reduce-add), see run_backward
-            ops.gemm(dy, x, f.g(wkey, shape=tuple(w.shape), numel=w.numel()), a_mn_major=True, b_mn_major=True,
+            ops.gemm(dy, x, self._wgrad_out(wkey, tuple(w.shape), w.numel()), a_mn_major=True, b_mn_major=True,
                      accumulate=self.wgrad_split, d_streamed=True, max_ctas=self.wgrad_ctas)
             if bias_grad:
                 bkey = wkey[:-len("weight")] + "bias"
                 ops.colsum(dy, f.g(bkey, numel=w.shape[0]))
         if dx is not None:
             ops.gemm(dy, w, dx, b_mn_major=True, aux=aux, aux_mode=aux_mode, b_streamed=True)
+
+    def _wgrad_out(self, wkey, shape, numel):
+        """Where a weight gradient is written: the fp32 flat gradient buffer, or -- with the switch transport -- the bf16
+        symmetric exchange buffer at the same offset (widened into the fp32 views after the all-reduce)."""
+        if self.comm_switch is None:
+            return self.flat.g(wkey, shape=shape, numel=numel)
+        o = self.flat.offsets[wkey]
+        return self.comm_switch.buf[o:o + numel].view(shape)
 
     def _side_stream(self, cur):
         pl = self._pl
@@ -505,7 +524,17 @@ class _Engine:
             self.comm_stream.wait_stream(s)
         ranges = ddp.merge_ranges(self._pending)
         with torch.cuda.stream(self.comm_stream):
-            ddp.all_reduce_mean_ranges(self.flat.grad, ranges, self.comm_group, self.comm_staging)
+            if self.comm_switch is not None:
+                sw, f = self.comm_switch, self.flat
+                for lo, hi in ranges:
+                    if hi > f.w_end:      # the small parameters were accumulated in fp32 (atomics): narrow that part once
+                        s0 = max(lo, f.w_end)
+                        ops.cast_bf16(f.grad[s0:hi], sw.buf[s0:hi])
+                    sw.all_reduce_mean(lo, hi)
+                    if sw.grad is None:                 # (else the fp32 mean has already landed in f.grad[lo:hi] on every rank)
+                        ops.cast_f32(sw.buf[lo:hi], f.grad[lo:hi])
+            else:
+                ddp.all_reduce_mean_ranges(self.flat.grad, ranges, self.comm_group, self.comm_staging)
         self._pending, self._pending_streams = [], set()
 
     def _next_site(self):
@@ -801,7 +830,7 @@ class _Engine:
             self._linear_bwd(g_s, pl.feat, ve + ".image_embeddings.weight", bias_grad=False)
             if pl.onehot_r is not None:     # d position table = onehot^T g_s: the ordinary weight-gradient contraction
                 n_pos = f.named[V_POS_KEY].shape[0]
-                ops.gemm(pl.onehot_r[:, :R], g_s, f.g(V_POS_KEY, shape=(n_pos, Hv), numel=n_pos * Hv)[:R], a_mn_major=True,
+                ops.gemm(pl.onehot_r[:, :R], g_s, self._wgrad_out(V_POS_KEY, (n_pos, Hv), n_pos * Hv)[:R], a_mn_major=True,
                          b_mn_major=True, d_streamed=True)
             ops.loc_embed_bwd(g_s, pl.loc, f.g(ve + ".image_location_embeddings.weight"),
                               f.g(ve + ".image_location_embeddings.bias"))

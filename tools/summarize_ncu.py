@@ -17,10 +17,13 @@ KEYS = [
     "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
-    "sm__inst_executed_pipe_tc.sum", "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_tc.sum", "sm__inst_executed_pipe_tc_scope_2cta.sum", "sm__mem_tensor_reads_op_ldt.sum", "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed.sum",
     "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "l1tex__data_bank_conflicts_pipe_lsu.sum",
     "smsp__cycles_active.avg", "sm__inst_executed_pipe_tma.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
 ]
 
 
@@ -53,12 +56,18 @@ def full(path):
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     print(f"# ncu --set full: {path} ({len(rows) - 2} launches)\n")
-    for r in rows[2:]:
+    body = rows[2:]
+    if len(sys.argv) > 3:          # keep every n-th launch (tools/prof_dominant.py: three warm-ups per shape)
+        n = int(sys.argv[3])
+        body = body[n - 1::n]
+    for r in body:
         print(f"## `{r[col['Kernel Name']][:120]}`  grid {r[col.get('Grid Size', 0)]} block {r[col.get('Block Size', 0)]}\n")
         print("| metric | value | unit |\n|---|---|---|")
         for k in KEYS:
-            if k in col:
-                print(f"| {k} | {r[col[k]]} | {units[col[k]]} |")
+            # some sm_100 counters come back under a unit prefix ("TPC.TriageCompute.sm__pipe_tensor_...")
+            hit = k if k in col else next((h for h in hdr if h.endswith("." + k)), None)
+            if hit is not None and r[col[hit]] not in ("", "n/a"):
+                print(f"| {hit} | {r[col[hit]]} | {units[col[hit]]} |")
         print()
 
 
