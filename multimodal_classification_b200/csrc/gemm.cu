@@ -398,8 +398,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   GemmKernelParams p = p_const;
   pin(p.bn); pin(p.stages); pin(p.d_is_f32); pin(p.has_preact); pin(p.nbuf); pin(p.pdl_late); pin(p.a_3d); pin(p.b_3d);
   // PDL: the next kernel of the stream may begin its own prologue; it blocks in griddepcontrol.wait until this grid is done.
-  // (pdl_late: the producer triggers it after its last load instead -- a dependent that has waited long in
-  // griddepcontrol.wait wakes up late.)
+  // pdl_late (default; VB_GEMM_PDL_LATE=0 for the early form): the producer triggers the dependent launch after its LAST load
+  // instead of at kernel entry -- a dependent that has sat long in griddepcontrol.wait wakes up late (4.73 -> 4.68 ms/step).
   if (!p.pdl_late) griddep_launch();
   pin(p.scale); pin(p.bias); pin(p.aux); pin(p.ld_aux); pin(p.m); pin(p.n); pin(p.k);
   pin(p.reduce_add); pin(p.act); pin(p.aux_mode);
@@ -719,12 +719,13 @@ static int num_sms() {
 }
 
 // experiment knobs: read once from the environment, overridable at run time through vb_gemm_set_knob (tools/gemm_mainloop.py)
-struct GemmKnobs { int occ1, max_bn, np, cg, debug_mode, stages, no_l2_hints, compact, pdl_late; };
+struct GemmKnobs { int occ1, max_bn, np, cg, debug_mode, stages, no_l2_hints, compact, pdl_late, smem_kb, max_stages, nbuf; };
 static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
 static GemmKnobs& knobs() {
   static GemmKnobs k = {env_int("VB_GEMM_OCC1", 0), env_int("VB_GEMM_MAX_BN", 256), env_int("VB_GEMM_NP", 0), env_int("VB_GEMM_CG", 0),
                         env_int("VB_GEMM_DEBUG", 0), env_int("VB_GEMM_STAGES", 0), env_int("VB_GEMM_NO_L2_HINTS", 0),
-                        env_int("VB_GEMM_COMPACT", 0), env_int("VB_GEMM_PDL_LATE", 0)};
+                        env_int("VB_GEMM_COMPACT", 0), env_int("VB_GEMM_PDL_LATE", 1), env_int("VB_GEMM_SMEM_KB", 0),
+                        env_int("VB_GEMM_MAX_STAGES", 10), env_int("VB_GEMM_NBUF", 2)};
   return k;
 }
 // Residency target per SM.  VB_GEMM_COMPACT (knob "compact"): 0 = one CTA per SM for every GEMM (default: deep operand ring,
@@ -785,15 +786,21 @@ static int max_clusters(int cs, int occupancy) {
   return cached[cs][occupancy];
 }
 
-static int gemm_nbuf(const vb_gemm_args& a, int bn) { return gemm_occupancy(a, bn) == 1 ? 2 : 1; }
+static int gemm_nbuf(const vb_gemm_args& a, int bn) { return (gemm_occupancy(a, bn) == 1 && knobs().nbuf == 2) ? 2 : 1; }
 static int gemm_stages(const vb_gemm_args& a, int bn, int cg) {
   const int occ = gemm_occupancy(a, bn);
   const int bnl = bn / cg;
   const GemmSmem z = gemm_smem(0, bnl, bn, a.d_is_f32 != 0, a.d_preact != nullptr, a.scale != nullptr, a.aux_mode != VB_AUX_NONE, gemm_nbuf(a, bn));
-  int stages = (gemm_smem_limit(occ) - 1024 /*alignment slack*/ - static_cast<int>(z.total)) / (GEMM_A_BYTES + bnl * 128);
-  // measured (tools/gemm_mainloop.py): the main loop runs at the same rate with 3 and with 8 stages; 6 leave room for the
-  // double-buffered epilogue and keep the footprint of a CTA (and its TMA traffic in flight) moderate
-  if (stages > 6) stages = 6;
+  // VB_GEMM_SMEM_KB: leave shared memory on the SM to co-resident blocks of other streams' kernels (LayerNorm backward, ...)
+  int limit = gemm_smem_limit(occ);
+  if (occ == 1 && knobs().smem_kb > 0 && knobs().smem_kb * 1024 < limit) limit = knobs().smem_kb * 1024;
+  int stages = (limit - 1024 /*alignment slack*/ - static_cast<int>(z.total)) / (GEMM_A_BYTES + bnl * 128);
+  // A kernel timed alone runs its main loop at the same rate with 3 and with 8 stages (tools/gemm_mainloop.py), but inside the
+  // training step, where four streams share L2 and HBM, the depth absorbs the latency jitter: 4 stages 5.08 ms/step, 6 -> 4.76,
+  // 8 -> 4.73, 10 -> 4.70 (VB_GEMM_MAX_STAGES)
+  int cap = knobs().max_stages;
+  if (cap > GEMM_MAX_STAGES) cap = GEMM_MAX_STAGES;
+  if (stages > cap) stages = cap;
   return stages;
 }
 
@@ -1043,7 +1050,8 @@ extern "C" int vb_gemm_set_knob(const char* name, int value) {
   GemmKnobs& k = knobs();
   const struct { const char* n; int* v; } tab[] = {{"occ1", &k.occ1}, {"max_bn", &k.max_bn}, {"np", &k.np}, {"cg", &k.cg},
                                                    {"debug_mode", &k.debug_mode}, {"stages", &k.stages}, {"no_l2_hints", &k.no_l2_hints},
-                                                   {"compact", &k.compact}, {"pdl_late", &k.pdl_late}};
+                                                   {"compact", &k.compact}, {"pdl_late", &k.pdl_late}, {"smem_kb", &k.smem_kb},
+                                                   {"max_stages", &k.max_stages}, {"nbuf", &k.nbuf}};
   for (const auto& e : tab)
     if (strcmp(e.n, name) == 0) { *e.v = value; return VB_OK; }
   vb_set_last_error("vb_gemm_set_knob", "unknown knob");
