@@ -407,7 +407,7 @@ def main():
     model.train(not args.eval_dropout_off)
     if world > 1 and os.environ.get("VB_DDP_SKIP", "0") != "1":      # VB_DDP_SKIP: diagnostic only (replicas without exchange)
         if os.environ.get("VB_DDP_FLUSH_MB"):
-            vb_ddp.FLUSH_BYTES = int(os.environ["VB_DDP_FLUSH_MB"]) << 20
+            vb_ddp.FLUSH_BYTES = vb_ddp.SWITCH_FLUSH_BYTES = int(os.environ["VB_DDP_FLUSH_MB"]) << 20
         # gradient exchange of the scaling runs: bf16 through our own NVSwitch kernels (multimem reduce in the switch; the weight-
         # gradient GEMMs write bf16 straight into the symmetric buffer).  VB_DDP_TRANSPORT=nccl: bucketed NCCL all-reduce of bf16
         # casts; VB_DDP_FP32=1: fp32 over NCCL (numerically the single-GPU step).  A box without symmetric-memory support falls

@@ -148,7 +148,8 @@ def attach(model, group=None, compress=None, transport: str = "nccl") -> None:
     model._engine = None
 
 
-FLUSH_BYTES = 160 << 20     # exchange finished buckets once this many gradient bytes are waiting
+FLUSH_BYTES = 160 << 20     # exchange finished buckets once this many gradient bytes are waiting (NCCL transport)
+SWITCH_FLUSH_BYTES = 80 << 20   # the same for the switch transport (fp32-equivalent bytes): its three launches cost ~30 us per message
 
 
 def merge_ranges(ranges):

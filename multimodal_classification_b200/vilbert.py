@@ -389,7 +389,9 @@ class _Engine:
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if self.comm_group is not None else None   # as urgent as the chain: NCCL CTAs must get SM slots while GEMMs are running
         self.comm_compress = getattr(model, "_ddp_compress", None) if self.comm_group is not None else None
         self.comm_switch = None
+        self.widen_stream = None
         if self.comm_group is not None and getattr(model, "_ddp_transport", "nccl") == "switch":
+            self.widen_stream = torch.cuda.Stream(device=device)      # bf16 -> fp32 of reduced ranges: HBM work, off the link stream
             from . import ddp
             # VB_DDP_FP32_BCAST=1: the fp32 gradient buffer becomes a symmetric buffer too and the reduce kernel broadcasts the
             # mean into it already widened.  Measured SLOWER at N = 2 (5.97 vs 5.55 ms/step): twice the bytes on the links,
@@ -518,7 +520,8 @@ class _Engine:
             self._pending.append(self.flat.buckets[name])
             self._pending_streams.update(producers)
         nbytes = sum(hi - lo for lo, hi in self._pending) * 4
-        if not self._pending or (not flush and nbytes < ddp.FLUSH_BYTES):
+        threshold = ddp.SWITCH_FLUSH_BYTES if self.comm_switch is not None else ddp.FLUSH_BYTES
+        if not self._pending or (not flush and nbytes < threshold):
             return
         for s in self._pending_streams:
             self.comm_stream.wait_stream(s)
@@ -532,7 +535,10 @@ class _Engine:
                         ops.cast_bf16(f.grad[s0:hi], sw.buf[s0:hi])
                     sw.all_reduce_mean(lo, hi)
                     if sw.grad is None:                 # (else the fp32 mean has already landed in f.grad[lo:hi] on every rank)
-                        ops.cast_f32(sw.buf[lo:hi], f.grad[lo:hi])
+                        # widen on its own stream: the next range's reduction (NVLink-bound) overlaps this HBM-bound pass
+                        self.widen_stream.wait_stream(self.comm_stream)
+                        with torch.cuda.stream(self.widen_stream):
+                            ops.cast_f32(sw.buf[lo:hi], f.grad[lo:hi])
             else:
                 ddp.all_reduce_mean_ranges(self.flat.grad, ranges, self.comm_group, self.comm_staging)
         self._pending, self._pending_streams = [], set()
@@ -849,6 +855,8 @@ class _Engine:
         self._bucket_ready("tail", [s_t], flush=True)
         if self.comm_stream is not None:
             s_t.wait_stream(self.comm_stream)
+        if self.widen_stream is not None:
+            s_t.wait_stream(self.widen_stream)
 
     @staticmethod
     def _co_index(text_layer):
