@@ -86,7 +86,6 @@ struct GemmKernelParams {
   int m_tiles, n_tiles;
   int stages;       // depth of the operand ring
   int nbuf;         // staging boxes per epilogue warp (1 | 2)
-  int a_3d, b_3d;   // the MN-major operand is fetched through a 3-D tensor map (64 | k | piece): one TMA instruction per tile
   int pdl_late;     // trigger the dependent launch when the producer is done instead of at kernel entry
   int tmem_cols;
   int debug_mode;   // profiling only (VB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads; results are garbage
@@ -170,23 +169,6 @@ __device__ __forceinline__ void tma_load_2d_warp(uint32_t dst, const CUtensorMap
   asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
                "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
                " [%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
-               : "memory");
-}
-// MN-major operand tiles are made of 64-wide pieces (one 128-byte swizzle row per k); through a 3-D view of the matrix
-// (64 | k | piece) ONE instruction fetches all pieces of a tile, so that the producer issues two TMA instructions per k-block
-// whatever the layout.  Kept as an experiment (VB_GEMM_3D=1): on B200 it measured slower than one 2-D load per piece.
-__device__ __forceinline__ void tma_load_3d_pair_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint64_t policy) {
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-               "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-               " [%0], [%1, {%3, %4, %5}], [%2], %6;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
-               "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, uint64_t policy) {
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
-               "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-               " [%0], [%1, {%3, %4, %5}], [%2], %6;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
-               "l"(policy)
                : "memory");
 }
 // every lane polls (same barrier, same answer: no divergence), so the code after the wait is still warp-uniform
@@ -292,8 +274,7 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
 template <bool A_MN, bool B_MN, int CG, int NP>
 __device__ __forceinline__ void issue_kblock(const CUtensorMap* tma_a, const CUtensorMap* tma_b, uint32_t sa, uint32_t sb,
                                              uint32_t full_bar, uint32_t bar_leader, int bnl, int k0, int m0, int n0,
-                                             uint32_t prank, uint32_t pair, uint16_t a_mask, unsigned long long b_policy, bool a3d,
-                                             bool b3d) {
+                                             uint32_t prank, uint32_t pair, uint16_t a_mask, unsigned long long b_policy) {
   const int b_bytes = bnl * GEMM_BK * 2;
   if constexpr (CG == 2) {
     // both CTAs' bytes are counted on the leader's barrier; a peer load that lands before the leader's expect_tx only
@@ -307,42 +288,26 @@ __device__ __forceinline__ void issue_kblock(const CUtensorMap* tma_a, const CUt
       if constexpr (A_MN) tma_load_2d_pair_mc_warp(sa + pair * (GEMM_BK * 128), tma_a, bar_leader, m0 + static_cast<int>(pair) * 64, k0, a_mask);
       else                tma_load_2d_pair_mc_warp(sa + pair * (64 * 128), tma_a, bar_leader, k0, m0 + static_cast<int>(pair) * 64, a_mask);
     } else if constexpr (A_MN) {
-      if (a3d) {
-        tma_load_3d_pair_warp(sa, tma_a, bar_leader, 0, k0, m0 >> 6, L2_EVICT_NORMAL);
-      } else {
 #pragma unroll
-        for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair_warp(sa + j * (GEMM_BK * 128), tma_a, bar_leader, m0 + j * 64, k0, L2_EVICT_NORMAL);
-      }
+      for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_pair_warp(sa + j * (GEMM_BK * 128), tma_a, bar_leader, m0 + j * 64, k0, L2_EVICT_NORMAL);
     } else {
       tma_load_2d_pair_warp(sa, tma_a, bar_leader, k0, m0, L2_EVICT_NORMAL);
     }
     if constexpr (B_MN) {
-      if (b3d) {
-        tma_load_3d_pair_warp(sb, tma_b, bar_leader, 0, k0, n0 >> 6, b_policy);
-      } else {
-        for (int j = 0; j < bnl / 64; ++j) tma_load_2d_pair_warp(sb + j * (GEMM_BK * 128), tma_b, bar_leader, n0 + j * 64, k0, b_policy);
-      }
+      for (int j = 0; j < bnl / 64; ++j) tma_load_2d_pair_warp(sb + j * (GEMM_BK * 128), tma_b, bar_leader, n0 + j * 64, k0, b_policy);
     } else {
       tma_load_2d_pair_warp(sb, tma_b, bar_leader, k0, n0, b_policy);
     }
   } else {
     mbar_arrive_expect_tx_warp(full_bar, static_cast<uint32_t>(GEMM_A_BYTES + b_bytes));
     if constexpr (A_MN) {
-      if (a3d) {
-        tma_load_3d_warp(sa, tma_a, full_bar, 0, k0, m0 >> 6, L2_EVICT_NORMAL);
-      } else {
 #pragma unroll
-        for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_warp(sa + j * (GEMM_BK * 128), tma_a, full_bar, m0 + j * 64, k0, L2_EVICT_NORMAL);
-      }
+      for (int j = 0; j < GEMM_BM / 64; ++j) tma_load_2d_warp(sa + j * (GEMM_BK * 128), tma_a, full_bar, m0 + j * 64, k0, L2_EVICT_NORMAL);
     } else {
       tma_load_2d_warp(sa, tma_a, full_bar, k0, m0, L2_EVICT_NORMAL);
     }
     if constexpr (B_MN) {
-      if (b3d) {
-        tma_load_3d_warp(sb, tma_b, full_bar, 0, k0, n0 >> 6, b_policy);
-      } else {
-        for (int j = 0; j < bnl / 64; ++j) tma_load_2d_warp(sb + j * (GEMM_BK * 128), tma_b, full_bar, n0 + j * 64, k0, b_policy);
-      }
+      for (int j = 0; j < bnl / 64; ++j) tma_load_2d_warp(sb + j * (GEMM_BK * 128), tma_b, full_bar, n0 + j * 64, k0, b_policy);
     } else {
       tma_load_2d_warp(sb, tma_b, full_bar, k0, n0, b_policy);
     }
@@ -396,7 +361,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #endif
 
   GemmKernelParams p = p_const;
-  pin(p.bn); pin(p.stages); pin(p.d_is_f32); pin(p.has_preact); pin(p.nbuf); pin(p.pdl_late); pin(p.a_3d); pin(p.b_3d);
+  pin(p.bn); pin(p.stages); pin(p.d_is_f32); pin(p.has_preact); pin(p.nbuf); pin(p.pdl_late);
   // PDL: the next kernel of the stream may begin its own prologue; it blocks in griddepcontrol.wait until this grid is done.
   // pdl_late (default; VB_GEMM_PDL_LATE=0 for the early form): the producer triggers the dependent launch after its LAST load
   // instead of at kernel entry -- a dependent that has sat long in griddepcontrol.wait wakes up late (4.73 -> 4.68 ms/step).
@@ -460,7 +425,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         issue_kblock<A_MN, B_MN, CG, NP>(&tma_a, &tma_b, sa0 + static_cast<uint32_t>(stage * GEMM_A_BYTES),
                                          sb0 + static_cast<uint32_t>(stage * B_BYTES), full0 + static_cast<uint32_t>(stage) * 8u,
                                          full_leader + static_cast<uint32_t>(stage) * 8u, BNL, kb * GEMM_BK, m0, n0, prank, pair,
-                                         a_mask, b_policy, p.a_3d != 0, p.b_3d != 0);
+                                         a_mask, b_policy);
         if (lane == 0 && tile == first_tile && kb == kb0) trace_stamp(3);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -811,22 +776,14 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   CUtensorMap map_a, map_b, map_d, map_x, map_aux;
   int rc;
   // K-major operand: global [rows, K] -> box {64 (k), rows_per_cta}; MN-major: global [K, rows] -> box {64 (mn), 64 (k)}
-  // An MN-major operand whose MN extent is a multiple of 64 is described as (64 | k | MN / 64): one box = every 64-wide piece
-  // of a tile (with a ragged last piece the flat 2-D description and one load per piece stay in use: a 3-D view would run
-  // over the row end instead of reading zeros).
-  // Opt-in (VB_GEMM_3D=1): measured SLOWER than one 2-D load per piece on B200 (weight gradients 1 031 -> 1 270 us per step,
-  // profiles/r02_gemm_experiments.md) -- the 3-D box with a 128-byte innermost extent is unpacked less efficiently by the TMA unit
-  // than the issue cost it saves.
-  static const bool use_3d = env_int("VB_GEMM_3D", 0) != 0;
-  const bool a_3d = A_MN && NP == 1 && a.m % 64 == 0 && use_3d;
-  const bool b_3d = B_MN && bnl > 64 && a.n % 64 == 0 && use_3d;
-  if (a_3d)      rc = make_tensor_map_3d(&map_a, a.a, 64, a.k, a.m / 64, a.lda, 64, 64, GEMM_BK, GEMM_BM / 64);
-  else if (A_MN) rc = make_tensor_map_2d(&map_a, a.a, /*inner*/ a.m, /*outer*/ a.k, a.lda, 64, GEMM_BK);
-  else           rc = make_tensor_map_2d(&map_a, a.a, a.k, a.m, a.lda, GEMM_BK, GEMM_BM / NP);   // NP = 2: multicast halves
+  // (Tried: describing an MN-major operand as a 3-D tensor (64 | k | piece) so that ONE instruction fetches every 64-wide piece
+  // of a tile.  Measured slower on B200 -- weight gradients 1 031 -> 1 270 us per step, profiles/r02_gemm_experiments.md -- and
+  // removed: one 2-D load per piece.)
+  if (A_MN) rc = make_tensor_map_2d(&map_a, a.a, /*inner*/ a.m, /*outer*/ a.k, a.lda, 64, GEMM_BK);
+  else      rc = make_tensor_map_2d(&map_a, a.a, a.k, a.m, a.lda, GEMM_BK, GEMM_BM / NP);   // NP = 2: multicast halves
   if (rc != VB_OK) return rc;
-  if (b_3d)      rc = make_tensor_map_3d(&map_b, a.b, 64, a.k, a.n / 64, a.ldb, 64, 64, GEMM_BK, bnl / 64);
-  else if (B_MN) rc = make_tensor_map_2d(&map_b, a.b, a.n, a.k, a.ldb, 64, GEMM_BK);
-  else           rc = make_tensor_map_2d(&map_b, a.b, a.k, a.n, a.ldb, GEMM_BK, bnl);
+  if (B_MN) rc = make_tensor_map_2d(&map_b, a.b, a.n, a.k, a.ldb, 64, GEMM_BK);
+  else      rc = make_tensor_map_2d(&map_b, a.b, a.k, a.n, a.ldb, GEMM_BK, bnl);
   if (rc != VB_OK) return rc;
   // epilogue boxes: 32 rows x 32 columns per warp (fp32: 128-byte rows, 128B swizzle; bf16: 64-byte rows, 64B swizzle)
   if (a.d_is_f32) rc = make_tensor_map_2d_f32(&map_d, a.d, a.n, a.m, a.ldd, GEMM_CHUNK, 32);
@@ -871,8 +828,6 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   int stages = gemm_stages(a, bn, CG);
   p.nbuf = gemm_nbuf(a, bn);
   p.pdl_late = knobs().pdl_late;
-  p.a_3d = a_3d ? 1 : 0;
-  p.b_3d = b_3d ? 1 : 0;
   if (stages < 2) {
     vb_set_last_error("vb_gemm_bf16", "tile configuration does not fit shared memory");
     return VB_ERR_UNSUPPORTED;
