@@ -317,12 +317,30 @@ int vb_avgpool_nhwc(const void* x, float* out, int32_t r, int32_t s, int32_t c, 
 
 /* Proposal selection (:251-293).  scores[i] = 1 - |((x2-x1)/img_w) * ((y2-y1)/img_h) - target_area| in the reference's fp32
  * operation order (:262-270); vb_nms = torchvision.ops.nms(boxes, scores, iou_threshold) (:277) with the CPU kernel's
- * semantics: stable descending sort of the scores, greedy suppression of IoU > threshold, kept indices in score order.
+ * semantics: stable descending sort of the scores, greedy suppression of IoU > threshold (fp32 IoU compared with the DOUBLE
+ * threshold, as torchvision does), kept indices in score order.
  * Bit-exact: the scores of translated copies of one box size tie exactly and the tie order decides which boxes survive.
  * boxes fp32 [n,4] (x1,y1,x2,y2); workspace int32 [2n]; keep int32 [n]; *num_keep int32 (all device). */
 int vb_box_area_score(const float* boxes, int32_t n, float img_w, float img_h, float target_area, float* scores, void* stream);
-int vb_nms(const float* boxes, const float* scores, int32_t n, float iou_threshold, int32_t* workspace, int32_t* keep,
+int vb_nms(const float* boxes, const float* scores, int32_t n, double iou_threshold, int32_t* workspace, int32_t* keep,
            int32_t* num_keep, void* stream);
+
+/* Visual Genome Faster R-CNN extractor (next-row f-4; models/feature_extractors/fasterrcnn_vg.py).
+ *   vb_rowmax_f32     : out[r] = max over columns [col_begin, col_end) of fp32 x[rows, ld] -- the proposal score
+ *                       ``cls_scores[:, 1:].max(dim=1)[0]`` of _score_proposals (:345-365; column 0 = background).
+ *   vb_select_regions : _select_top_regions + _pad_regions + _extract_roi_features' row choice + _normalize_boxes
+ *                       (:367-411, 436-469) on the device, no host round trip: output region r is candidate
+ *                       keep[min(r, *num_keep - 1)] (vb_nms leaves the survivors in descending score order, so the
+ *                       reference's top-k over them is their first `regions` entries; among exactly tied scores torch.topk's
+ *                       order is unspecified and the stable order is kept).  Writes, each optional (NULL): boxes fp32
+ *                       [regions,4], spatial fp32 [regions,5] = (x1/img_w, y1/img_h, x2/img_w, y2/img_h clamped to [0,1],
+ *                       area) bit-exact with the reference's fp32 tensor ops, index int32 [regions], and feat_dst fp32
+ *                       [regions, feat_dim] = rows of feat_src [n, feat_dim], rois fp32 [regions,5] = (batch_index, box): the
+ *                       vb_roi_pool_nhwc operand of the chosen boxes.  *num_keep == 0 leaves the outputs untouched. */
+int vb_rowmax_f32(const float* x, int32_t rows, int32_t ld, int32_t col_begin, int32_t col_end, float* out, void* stream);
+int vb_select_regions(const float* candidates, const int32_t* keep, const int32_t* num_keep, int32_t regions, float img_w,
+                      float img_h, const float* feat_src, int32_t feat_dim, float* boxes, float* spatial, float* feat_dst,
+                      int32_t* index, float* rois, float batch_index, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DINOv2 multi-layer fusion tail (next-row f-2; models/feature_extractors/dinov2_multilayer.py:342-381).

@@ -152,7 +152,9 @@ def _declare(l: C.CDLL) -> None:
         "vb_grad_sumsq": [vp, i64, vp, vp],
         "vb_adamw_step": [C.POINTER(AdamWArgs), vp],
         "vb_box_area_score": [vp, i32, f32, f32, f32, vp, vp],
-        "vb_nms": [vp, vp, i32, f32, vp, vp, vp, vp],
+        "vb_nms": [vp, vp, i32, C.c_double, vp, vp, vp, vp],
+        "vb_rowmax_f32": [vp, i32, i32, i32, i32, vp, vp],
+        "vb_select_regions": [vp, vp, vp, i32, f32, f32, vp, i32, vp, vp, vp, vp, vp, f32, vp],
         "vb_lmdb_regions": [vp, vp, i64, vp, vp, i32, i32, f32, f32, vp],
         "vb_attn_merge": [vp, vp, i32, i64, vp, i64, vp, i32, i32, i32, i64, i32, vp],
         "vb_attn_delta": [vp, i64, vp, i64, vp, i32, i32, i32, i64, i32, vp],

@@ -561,6 +561,47 @@ def nms(boxes, scores, iou_threshold):
     return keep[:int(cnt.item())].long()
 
 
+def nms_device(boxes, scores, iou_threshold, workspace, keep, num_keep):
+    """vb_nms without the host read of the survivor count (graph-capturable): keep int32 [n] / num_keep int32 [1] stay on the
+    device for ``select_regions``."""
+    _need_cuda(boxes, scores, workspace, keep, num_keep)
+    n = boxes.shape[0]
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and scores.dtype == torch.float32 and scores.is_contiguous()
+    assert workspace.dtype == torch.int32 and workspace.numel() >= 2 * n and keep.dtype == torch.int32 and keep.numel() >= n
+    assert num_keep.dtype == torch.int32 and scores.numel() == n
+    _lib.check(_lib.lib().vb_nms(boxes.data_ptr(), scores.data_ptr(), n, float(iou_threshold), workspace.data_ptr(),
+                                 keep.data_ptr(), num_keep.data_ptr(), _stream()), "vb_nms")
+    return keep, num_keep
+
+
+def rowmax(x, out, col_begin=0, col_end=None):
+    """out[r] = max(x[r, col_begin:col_end]) over fp32 rows (fasterrcnn_vg.py:360-363)."""
+    _need_cuda(x, out)
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.stride(1) == 1 and out.numel() == x.shape[0]
+    col_end = x.shape[1] if col_end is None else col_end
+    _lib.check(_lib.lib().vb_rowmax_f32(x.data_ptr(), x.shape[0], x.stride(0), col_begin, col_end, out.data_ptr(), _stream()),
+               "vb_rowmax_f32")
+    return out
+
+
+def select_regions(candidates, keep, num_keep, regions, img_w, img_h, *, boxes=None, spatial=None, index=None, feat_src=None,
+                   feat_dst=None, rois=None, batch_index=0):
+    """Region r <- candidate keep[min(r, num_keep - 1)]: box, normalised spatial row, feature row (fasterrcnn_vg.py:367-469)."""
+    _need_cuda(candidates, keep, num_keep, boxes, spatial, index, feat_src, feat_dst, rois)
+    assert candidates.dtype == torch.float32 and candidates.is_contiguous() and keep.dtype == torch.int32
+    for t, width in ((boxes, 4), (spatial, 5), (rois, 5)):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (regions, width))
+    assert index is None or (index.dtype == torch.int32 and index.numel() == regions)
+    dim = 0
+    if feat_src is not None:
+        dim = feat_src.shape[1]
+        assert feat_src.dtype == torch.float32 and feat_dst.dtype == torch.float32 and feat_src.is_contiguous()
+        assert feat_dst.is_contiguous() and tuple(feat_dst.shape) == (regions, dim)
+    _lib.check(_lib.lib().vb_select_regions(candidates.data_ptr(), keep.data_ptr(), num_keep.data_ptr(), regions, float(img_w),
+                                            float(img_h), _ptr(feat_src), dim, _ptr(boxes), _ptr(spatial), _ptr(feat_dst),
+                                            _ptr(index), _ptr(rois), float(batch_index), _stream()), "vb_select_regions")
+
+
 def lmdb_regions(features=None, features_bf16=None, boxes=None, spatial=None, box_div=1000.0, area_div=1000000.0, stream=None):
     """Raw LMDB batch -> encoder inputs in one launch: fp32 features -> bf16; raw boxes [rows, >=4] -> spatial [rows, 5]
     (lmdb_dataset.py:189-208, bit-exact).  Either half may be omitted."""

@@ -148,7 +148,7 @@ def nms(boxes: np.ndarray, scores: np.ndarray, thr: float) -> np.ndarray:
         h = np.maximum(np.float32(0), yy2 - yy1)
         inter = w * h
         ovr = inter / (areas[i] + areas[rest] - inter)
-        suppressed[rest[ovr > np.float32(thr)]] = True
+        suppressed[rest[ovr.astype(np.float64) > float(thr)]] = True      # the C++ kernel's threshold is a double
     return np.asarray(keep, dtype=np.int64)
 
 
@@ -309,3 +309,100 @@ def grid_features(sd, img: torch.Tensor, num_regions: int = 36, output_dim: int 
     if f.shape[-1] < output_dim:
         f = torch.cat([f, torch.zeros(f.shape[0], output_dim - f.shape[-1])], dim=-1)
     return f[:, :output_dim].numpy()
+
+
+# ------------------------------------------------------------------------------------------------ VG Faster R-CNN extractor (f-4)
+VG_CLASSES = 1601
+
+
+def seeded_vg_heads(seed: int = 11) -> Dict[str, torch.Tensor]:
+    """Seeded stand-ins for the Visual Genome checkpoint's ``RCNN_cls_score`` / ``RCNN_bbox_pred`` heads
+    (fasterrcnn_vg.py:75-76); the class weights are wide enough that proposal scores are well separated."""
+    g = torch.Generator().manual_seed(seed)
+    return {"RCNN_cls_score.weight": torch.randn(VG_CLASSES, 2048, generator=g) * 0.05,
+            "RCNN_cls_score.bias": (torch.rand(VG_CLASSES, generator=g) - 0.5) * 0.1,
+            "RCNN_bbox_pred.weight": torch.randn(VG_CLASSES * 4, 2048, generator=g) * 0.001,
+            "RCNN_bbox_pred.bias": torch.zeros(VG_CLASSES * 4)}
+
+
+def vg_grid_candidates(img_h: int, img_w: int, num_proposals: int = 100) -> np.ndarray:
+    """fasterrcnn_vg.py:283-343: 5 scales x 3 aspect ratios, stride half a box, at most 2 * num_proposals candidates (the
+    inner ``break`` fires AFTER the append that reaches the limit and the y advance), grid cells appended when fewer than
+    num_proposals came out; Python-double accumulation, one rounding to fp32."""
+    rows: List[List[float]] = []
+    limit = num_proposals * 2
+    for scale in (0.2, 0.3, 0.4, 0.5, 0.7):
+        for ar in (0.5, 1.0, 2.0):
+            box_w = img_w * scale
+            box_h = box_w / ar
+            box_h = min(box_h, img_h * 0.9)
+            box_w = min(box_w, img_w * 0.9)
+            stride_x, stride_y = max(box_w * 0.5, 1), max(box_h * 0.5, 1)
+            x = 0
+            while x + box_w <= img_w:
+                y = 0
+                while y + box_h <= img_h:
+                    rows.append([x, y, x + box_w, y + box_h])
+                    y += stride_y
+                    if len(rows) >= limit:
+                        break
+                x += stride_x
+                if len(rows) >= limit:
+                    break
+            if len(rows) >= limit:
+                break
+        if len(rows) >= limit:
+            break
+    if len(rows) < num_proposals:
+        grid = int((num_proposals - len(rows)) ** 0.5) + 1
+        cell_w, cell_h = img_w / grid, img_h / grid
+        for i in range(grid):
+            for j in range(grid):
+                rows.append([j * cell_w, i * cell_h, min((j + 1) * cell_w, img_w), min((i + 1) * cell_h, img_h)])
+    return np.array(rows[:limit], dtype=np.float32).reshape(-1, 4)
+
+
+def vg_select(boxes: np.ndarray, scores: np.ndarray, num_regions: int, nms_thr: float) -> np.ndarray:
+    """fasterrcnn_vg.py:367-411 (``_select_top_regions`` + ``_pad_regions``): indices into ``boxes`` of the chosen regions.
+    ``nms`` returns the survivors in descending score order, so the reference's ``topk`` over them is their first
+    ``num_regions`` entries whenever the scores are distinct; among exactly tied scores torch.topk's order is unspecified and
+    this restatement keeps the stable (index) order."""
+    n = len(boxes)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64)
+    idx = np.arange(n, dtype=np.int64)
+    if n > num_regions:
+        idx = nms(boxes, scores, nms_thr)[:num_regions]
+    if len(idx) < num_regions:
+        idx = np.concatenate([idx, np.full(num_regions - len(idx), idx[-1], dtype=np.int64)])
+    return idx[:num_regions]
+
+
+def vg_scores(sd, heads, fmap: torch.Tensor, boxes: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """fasterrcnn_vg.py:345-365 (``_score_proposals``): RoIPool-14 -> layer4 -> mean -> class scores -> max over the 1600
+    object classes (background column 0 excluded).  Returns (scores [n], top features [n, 2048])."""
+    rois = np.concatenate([np.zeros((len(boxes), 1), np.float32), boxes], axis=1)
+    with torch.no_grad():
+        pooled = roi_pool(fmap.numpy(), rois, 14, 1.0 / 16.0)
+        top = forward_top(sd, torch.from_numpy(pooled))
+        cls = F.linear(top, heads["RCNN_cls_score.weight"], heads["RCNN_cls_score.bias"])
+    return cls[:, 1:].max(dim=1)[0].numpy(), top.numpy()
+
+
+def vg_extract_features(sd, heads, img: torch.Tensor, num_regions: int = 36, nms_thr: float = 0.3,
+                        has_vg_weights: bool = True, scores: np.ndarray = None):
+    """fasterrcnn_vg.py:252-281 on a preprocessed image [1,3,H,W]: (features [N,2048], spatial [N,5], boxes [N,4], candidate
+    scores).  ``sd`` uses the RoI backbone's key names with ResNet-101 block counts; ``scores`` overrides the candidate scores
+    (selection parity under given scores)."""
+    h, w = img.shape[2], img.shape[3]
+    with torch.no_grad():
+        fmap = forward_base(sd, img)
+    cands = vg_grid_candidates(h, w)
+    if scores is None:
+        scores = vg_scores(sd, heads, fmap, cands)[0] if has_vg_weights else np.ones(len(cands), np.float32)
+    idx = vg_select(cands, scores, num_regions, nms_thr)
+    boxes = cands[idx]
+    rois = np.concatenate([np.zeros((len(boxes), 1), np.float32), boxes], axis=1)
+    with torch.no_grad():
+        feats = forward_top(sd, torch.from_numpy(roi_pool(fmap.numpy(), rois, 14, 1.0 / 16.0))).numpy()
+    return feats, normalize_boxes(boxes, w, h), boxes, scores

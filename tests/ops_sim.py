@@ -322,8 +322,45 @@ def nms(boxes, scores, iou_threshold):
     return torchvision.ops.nms(boxes, scores, iou_threshold)
 
 
+def nms_device(boxes, scores, iou_threshold, workspace, keep, num_keep):
+    import torchvision
+    k = torchvision.ops.nms(boxes, scores, iou_threshold)
+    keep[: k.numel()] = k.to(torch.int32)
+    num_keep.fill_(k.numel())
+    return keep, num_keep
+
+
+def rowmax(x, out, col_begin=0, col_end=None):
+    out.copy_(x[:, col_begin:col_end].max(dim=1)[0])
+    return out
+
+
+def select_regions(candidates, keep, num_keep, regions, img_w, img_h, *, boxes=None, spatial=None, index=None, feat_src=None,
+                   feat_dst=None, rois=None, batch_index=0):
+    nk = int(num_keep.reshape(-1)[0])
+    if nk <= 0:
+        return
+    idx = keep[torch.arange(regions).clamp(max=nk - 1)].long()
+    b = candidates[idx]
+    if boxes is not None:
+        boxes.copy_(b)
+    if index is not None:
+        index.copy_(idx.to(torch.int32))
+    if rois is not None:
+        rois[:, 0] = float(batch_index)
+        rois[:, 1:] = b
+    if spatial is not None:
+        nb = b.clone()
+        nb[:, [0, 2]] /= img_w
+        nb[:, [1, 3]] /= img_h
+        nb = nb.clamp(0, 1)
+        spatial.copy_(torch.cat([nb, ((nb[:, 2] - nb[:, 0]) * (nb[:, 3] - nb[:, 1])).unsqueeze(1)], dim=1))
+    if feat_src is not None:
+        feat_dst.copy_(feat_src[idx])
+
+
 ROI_SIMULATED = ["stem_im2col", "im2col_nhwc", "maxpool_nhwc", "roi_pool_nhwc", "roi_align_nhwc", "avgpool_nhwc", "box_area_score",
-                 "nms"]
+                 "nms", "nms_device", "rowmax", "select_regions"]
 SIMULATED = ["gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "colsum", "cast_bf16", "cast_f32", "mask_bias",
              "i64_to_i32", "stage_batch", "dropout", "seed_advance", "act_bwd", "loc_embed_fwd", "loc_embed_bwd", "cls_ce_fwd", "cls_ce_bwd",
              "attention_fwd", "attention_bwd"]
