@@ -429,11 +429,11 @@ def main():
 
     params = list(model.parameters())
 
-    def step(batch):
+    def step(batch, mark=True):
         for p in params:            # what optimizer.zero_grad() does in the reference loop (nodes.py:784); Module.zero_grad
             p.grad = None           # re-walks the module tree every call and costs 0.7 ms of host time here
-        if model._engine is not None:
-            model._engine.flat._version = -1      # weights change every real training step: refresh the bf16 shadows
+        if mark:
+            model.parameters_updated()            # weights change every real training step: refresh the bf16 shadows
         out = model(**batch)
         out["loss"].backward()
         return out["loss"]
@@ -480,8 +480,11 @@ def main():
 
     # ---- end to end through the public API with host buffers: H2D of the batch and D2H of the loss inside the region
     def e2e_step():
+        # "the optimizer has stepped" is marked where optimizer.step() sits in the reference's loop (nodes.py:795-799): before
+        # the next batch is copied, so the shadow refresh may run beside that copy (torch optimizers mark it by a hook)
+        model.parameters_updated()
         dev_batch = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
-        loss = step(dev_batch)
+        loss = step(dev_batch, mark=False)
         return loss.item()
     for _ in range(3):
         e2e_step()

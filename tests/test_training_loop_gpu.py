@@ -118,6 +118,49 @@ def test_reference_training_loop_on_the_dropin_matches_the_fp32_oracle():
     assert torch.equal(eng.flat.w(key), master.to(torch.bfloat16))
 
 
+def test_shadow_refresh_beside_the_next_copy_follows_every_kind_of_update():
+    """The optimizer post-step hook marks "parameters updated" on the stream; the next forward refreshes the bf16 shadows on
+    a side stream ordered after THAT point (beside the next batch's host-to-device copy).  Whatever wrote the parameters --
+    torch optimizer, a manual in-place edit after the hook, ``parameters_updated()`` -- the shadow the forward reads must be
+    the bf16 rounding of the master at forward time."""
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    cfg = vo.tiny_config()
+    sd = vo.seeded_state_dict(cfg)
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    host = vo.synthetic_batch(cfg, batch=4, seq=32, regions=16, seed=9)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    key = "bert.encoder.layer.0.intermediate.dense.weight"
+    p = dict(model.named_parameters())[key]
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    model(**{k: v.cuda() for k, v in host.items()})["loss"].backward()
+    flat = model._engine.flat
+    assert model._engine.refresh_stream is not None
+    for step in range(3):
+        opt.step()
+        assert flat._updated is not None and flat._updated[1] == flat.versions()      # the hook fired
+        if step == 1:
+            with torch.no_grad():
+                p.mul_(1.5)                                   # an edit AFTER the hook: the side-stream path must not be taken
+            assert flat._updated[1] != flat.versions()
+        opt.zero_grad()
+        batch = {k: v.to("cuda", non_blocking=True) for k, v in pinned.items()}      # queued between the update and the forward
+        out = model(**batch)
+        assert flat._updated is None
+        assert torch.equal(flat.w(key), p.detach().to(torch.bfloat16)), step
+        ref = vo.forward({k: v.detach().cpu() for k, v in model.state_dict().items()}, cfg, **host)
+        assert abs(out["loss"].item() - ref["loss"].item()) <= 2e-3, step
+        out["loss"].backward()
+    # a hand-written update through the raw buffer (no version bump): parameters_updated()
+    with torch.no_grad():
+        flat.master[: flat.w_end].mul_(0.5)
+    model.parameters_updated()
+    with torch.no_grad():
+        model(**{k: v.cuda() for k, v in host.items()})
+    assert torch.equal(flat.w(key), p.detach().to(torch.bfloat16))
+
+
 def test_zero_grad_in_place_takes_the_fast_path_and_accumulation_still_adds():
     """zero_grad(set_to_none=False) through the module clears the flat buffer once and the next backward carries nothing;
     two backwards without clearing accumulate (p.grad = g1 + g2), as autograd would."""
