@@ -74,6 +74,11 @@ typedef struct vb_gemm_args {
   int32_t max_ctas;    /* 0 = all SMs; otherwise cap the persistent grid (stream co-scheduling) */
   int32_t b_streamed;  /* B is read once per step (a weight matrix): load it with the L2 evict-first hint */
   int32_t d_streamed;  /* D is not re-read soon (a weight gradient): store it with the L2 evict-first hint */
+  /* Implicit-GEMM convolution (conv_kh > 0; nn.Conv2d of the ResNet trunk, resnet152_roi.py:49-74): `a` is the bf16 NHWC
+   * activation [conv_n, conv_h, conv_w, conv_c] (contiguous, conv_c % 64 == 0), `b` the weight [n, conv_kh*conv_kw*conv_c] with
+   * column (ky*kw + kx)*c + ci, d the NHWC output [conv_n*ho*wo, n]; m = conv_n*ho*wo, k = conv_kh*conv_kw*conv_c, lda unused.
+   * The A tiles are fetched by TMA in im2col mode (zero padding by out-of-bounds fill): no [pixels, kh*kw*c] buffer exists. */
+  int32_t conv_n, conv_h, conv_w, conv_c, conv_kh, conv_kw, conv_stride, conv_pad;
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, void* stream);

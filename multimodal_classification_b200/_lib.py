@@ -30,6 +30,8 @@ class GemmArgs(C.Structure):
         ("d_is_f32", C.c_int32), ("accumulate", C.c_int32), ("act", C.c_int32), ("aux_mode", C.c_int32),
         ("block_n", C.c_int32), ("splits", C.c_int32), ("max_ctas", C.c_int32),
         ("b_streamed", C.c_int32), ("d_streamed", C.c_int32),
+        ("conv_n", C.c_int32), ("conv_h", C.c_int32), ("conv_w", C.c_int32), ("conv_c", C.c_int32),
+        ("conv_kh", C.c_int32), ("conv_kw", C.c_int32), ("conv_stride", C.c_int32), ("conv_pad", C.c_int32),
     ]
 
 

@@ -92,6 +92,10 @@ struct GemmKernelParams {
   uint32_t magic_m, magic_mn;   // fast_div multipliers for m_tiles and m_tiles * n_tiles
   unsigned long long b_policy, d_policy;   // L2 eviction hints for the B loads / D stores
   long long* trace; // profiling only (vb_gemm_set_trace): clock64 stamps per CTA, NULL in production
+  // implicit-GEMM convolution (CONV kernels): A is an NHWC activation read through an im2col tensor map
+  int conv_hw_out, conv_w_out;     // output pixels per image / per row
+  int conv_stride, conv_pad, conv_kw;
+  int conv_cblocks;                // 64-channel blocks per filter tap (c / 64)
 };
 
 // compiled in only with -DVB_GEMM_TRACE (__graft_entry__.build_variant builds that copy of the library): even a
@@ -169,6 +173,32 @@ __device__ __forceinline__ void tma_load_2d_warp(uint32_t dst, const CUtensorMap
   asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
                "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
                " [%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+               : "memory");
+}
+// im2col-mode loads (implicit-GEMM convolution): `pixels` consecutive output pixels x 64 channels of filter tap (ox, oy),
+// starting at the output pixel whose base input position is (w, h) of image n; same shared-memory layout as a K-major box
+__device__ __forceinline__ void tma_load_im2col_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n,
+                                                     uint16_t ox, uint16_t oy) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c),
+               "r"(w), "r"(h), "r"(n), "h"(ox), "h"(oy)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_pair_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h, int n,
+                                                          uint16_t ox, uint16_t oy) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c),
+               "r"(w), "r"(h), "r"(n), "h"(ox), "h"(oy)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_pair_mc_warp(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h,
+                                                             int n, uint16_t ox, uint16_t oy, uint16_t mask) {
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+               "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster"
+               " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;\n\t}" ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar),
+               "r"(c), "r"(w), "r"(h), "r"(n), "h"(ox), "h"(oy), "h"(mask)
                : "memory");
 }
 // every lane polls (same barrier, same answer: no divergence), so the code after the wait is still warp-uniform
@@ -314,7 +344,28 @@ __device__ __forceinline__ void issue_kblock(const CUtensorMap* tma_a, const CUt
   }
 }
 
-template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI>
+// The same for an implicit-GEMM convolution: A = one filter tap (kx, ky) x 64 channels [c0, c0 + 64) of this CTA's output
+// pixels, fetched in im2col mode from the NHWC activation (base input position (bw, bh) of image bn_img); B K-major as above.
+template <int CG, int NP>
+__device__ __forceinline__ void issue_kblock_conv(const CUtensorMap* tma_a, const CUtensorMap* tma_b, uint32_t sa, uint32_t sb,
+                                                  uint32_t full_bar, uint32_t bar_leader, int bnl, int k0, int n0, uint32_t prank,
+                                                  uint32_t pair, uint16_t a_mask, unsigned long long b_policy, int c0, int bw, int bh,
+                                                  int img, int kx, int ky) {
+  const int b_bytes = bnl * GEMM_BK * 2;
+  const uint16_t ox = static_cast<uint16_t>(kx), oy = static_cast<uint16_t>(ky);
+  if constexpr (CG == 2) {
+    if (prank == 0) mbar_arrive_expect_tx_warp(full_bar, static_cast<uint32_t>(2 * (GEMM_A_BYTES + b_bytes)));
+    if constexpr (NP == 2) tma_load_im2col_pair_mc_warp(sa + pair * (64 * 128), tma_a, bar_leader, c0, bw, bh, img, ox, oy, a_mask);
+    else                   tma_load_im2col_pair_warp(sa, tma_a, bar_leader, c0, bw, bh, img, ox, oy);
+    tma_load_2d_pair_warp(sb, tma_b, bar_leader, k0, n0, b_policy);
+  } else {
+    mbar_arrive_expect_tx_warp(full_bar, static_cast<uint32_t>(GEMM_A_BYTES + b_bytes));
+    tma_load_im2col_warp(sa, tma_a, full_bar, c0, bw, bh, img, ox, oy);
+    tma_load_2d_warp(sb, tma_b, full_bar, k0, n0, b_policy);
+  }
+}
+
+template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI, bool CONV = false>
 __global__ void __launch_bounds__(GEMM_THREADS, OCC)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_x,
@@ -411,6 +462,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const int n0 = (tc.n_idx * NP + static_cast<int>(pair)) * BN + static_cast<int>(prank) * BNL;
       const int kb0 = tc.split * p.kb_per_split;
       const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+      // implicit-GEMM convolution: where this CTA's first output pixel sits (once per tile), then (tap, channel block) counters
+      int cv_img = 0, cv_bw = 0, cv_bh = 0, cv_c = 0, cv_kx = 0, cv_ky = 0;
+      if constexpr (CONV) {
+        const int pix = m0 + (NP == 2 ? static_cast<int>(pair) * 64 : 0);
+        cv_img = pix / p.conv_hw_out;
+        const int r = pix - cv_img * p.conv_hw_out;
+        const int oy = r / p.conv_w_out;
+        cv_bh = oy * p.conv_stride - p.conv_pad;
+        cv_bw = (r - oy * p.conv_w_out) * p.conv_stride - p.conv_pad;
+        const int tap = kb0 / p.conv_cblocks;
+        cv_c = kb0 - tap * p.conv_cblocks;
+        cv_ky = tap / p.conv_kw;
+        cv_kx = tap - cv_ky * p.conv_kw;
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         if (fills >= STAGES) mbar_wait_addr(empty0 + static_cast<uint32_t>(stage) * 8u, phase ^ 1u);   // the first pass over the ring needs no wait
         ++fills;
@@ -422,10 +487,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           continue;
         }
 #endif
-        issue_kblock<A_MN, B_MN, CG, NP>(&tma_a, &tma_b, sa0 + static_cast<uint32_t>(stage * GEMM_A_BYTES),
-                                         sb0 + static_cast<uint32_t>(stage * B_BYTES), full0 + static_cast<uint32_t>(stage) * 8u,
-                                         full_leader + static_cast<uint32_t>(stage) * 8u, BNL, kb * GEMM_BK, m0, n0, prank, pair,
-                                         a_mask, b_policy);
+        if constexpr (CONV) {
+          issue_kblock_conv<CG, NP>(&tma_a, &tma_b, sa0 + static_cast<uint32_t>(stage * GEMM_A_BYTES),
+                                    sb0 + static_cast<uint32_t>(stage * B_BYTES), full0 + static_cast<uint32_t>(stage) * 8u,
+                                    full_leader + static_cast<uint32_t>(stage) * 8u, BNL, kb * GEMM_BK, n0, prank, pair, a_mask,
+                                    b_policy, cv_c * GEMM_BK, cv_bw, cv_bh, cv_img, cv_kx, cv_ky);
+          if (++cv_c == p.conv_cblocks) { cv_c = 0; if (++cv_kx == p.conv_kw) { cv_kx = 0; ++cv_ky; } }
+        } else {
+          issue_kblock<A_MN, B_MN, CG, NP>(&tma_a, &tma_b, sa0 + static_cast<uint32_t>(stage * GEMM_A_BYTES),
+                                           sb0 + static_cast<uint32_t>(stage * B_BYTES), full0 + static_cast<uint32_t>(stage) * 8u,
+                                           full_leader + static_cast<uint32_t>(stage) * 8u, BNL, kb * GEMM_BK, m0, n0, prank, pair,
+                                           a_mask, b_policy);
+        }
         if (lane == 0 && tile == first_tile && kb == kb0) trace_stamp(3);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -699,7 +772,7 @@ static GemmKnobs& knobs() {
 // bf16 outputs only.
 static int gemm_occupancy(const vb_gemm_args& a, int bn) {
   const int mode = knobs().occ1 ? 0 : knobs().compact;
-  if (bn > 128 || mode == 0) return 1;
+  if (bn > 128 || mode == 0 || a.conv_kh > 0) return 1;
   if (mode == 2) return a.d_is_f32 ? 2 : 1;
   if (mode == 3) return a.d_is_f32 ? 1 : 2;
   return 2;
@@ -769,8 +842,9 @@ static int gemm_stages(const vb_gemm_args& a, int bn, int cg) {
   return stages;
 }
 
-template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI>
+template <bool A_MN, bool B_MN, int CG, int NP, int OCC, int EPI, bool CONV = false>
 static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t stream) {
+  static_assert(!CONV || (!A_MN && !B_MN), "implicit-GEMM convolutions read K-major operands");
   constexpr int CS = CG * NP;
   const int bnl = bn / CG;
   CUtensorMap map_a, map_b, map_d, map_x, map_aux;
@@ -779,8 +853,10 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   // (Tried: describing an MN-major operand as a 3-D tensor (64 | k | piece) so that ONE instruction fetches every 64-wide piece
   // of a tile.  Measured slower on B200 -- weight gradients 1 031 -> 1 270 us per step, profiles/r02_gemm_experiments.md -- and
   // removed: one 2-D load per piece.)
-  if (A_MN) rc = make_tensor_map_2d(&map_a, a.a, /*inner*/ a.m, /*outer*/ a.k, a.lda, 64, GEMM_BK);
-  else      rc = make_tensor_map_2d(&map_a, a.a, a.k, a.m, a.lda, GEMM_BK, GEMM_BM / NP);   // NP = 2: multicast halves
+  if (CONV)      rc = make_tensor_map_im2col(&map_a, a.a, a.conv_n, a.conv_h, a.conv_w, a.conv_c, a.conv_kh, a.conv_kw, a.conv_stride,
+                                             a.conv_pad, GEMM_BM / NP);
+  else if (A_MN) rc = make_tensor_map_2d(&map_a, a.a, /*inner*/ a.m, /*outer*/ a.k, a.lda, 64, GEMM_BK);
+  else           rc = make_tensor_map_2d(&map_a, a.a, a.k, a.m, a.lda, GEMM_BK, GEMM_BM / NP);   // NP = 2: multicast halves
   if (rc != VB_OK) return rc;
   if (B_MN) rc = make_tensor_map_2d(&map_b, a.b, a.n, a.k, a.ldb, 64, GEMM_BK);
   else      rc = make_tensor_map_2d(&map_b, a.b, a.k, a.n, a.ldb, GEMM_BK, bnl);
@@ -803,6 +879,12 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   }
 
   GemmKernelParams p;
+  p.conv_hw_out = p.conv_w_out = p.conv_cblocks = p.conv_kw = 1; p.conv_stride = 1; p.conv_pad = 0;
+  if (CONV) {
+    const int ho = (a.conv_h + 2 * a.conv_pad - a.conv_kh) / a.conv_stride + 1, wo = (a.conv_w + 2 * a.conv_pad - a.conv_kw) / a.conv_stride + 1;
+    p.conv_hw_out = ho * wo; p.conv_w_out = wo; p.conv_stride = a.conv_stride; p.conv_pad = a.conv_pad; p.conv_kw = a.conv_kw;
+    p.conv_cblocks = a.conv_c / GEMM_BK;
+  }
   p.scale = a.scale; p.bias = a.bias;
   p.aux = static_cast<const __nv_bfloat16*>(a.aux); p.ld_aux = a.ld_aux;
   p.m = a.m; p.n = a.n; p.k = a.k;
@@ -846,7 +928,7 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   const int smem_bytes = 1024 + static_cast<int>(L.total);
 
   static bool attr_set = false;   // one per instantiation
-  auto kern = gemm_bf16_kernel<A_MN, B_MN, CG, NP, OCC, EPI>;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, CG, NP, OCC, EPI, CONV>;
   if (!attr_set) {
     VB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_limit(OCC)));
     attr_set = true;
@@ -953,6 +1035,10 @@ static int pick_epilogue(const vb_gemm_args& a) {
 template <int CG, int NP, int OCC>
 static int dispatch_major(const vb_gemm_args& a, int bn, int splits, cudaStream_t s) {
   const int epi = CG == 2 ? pick_epilogue(a) : EPI_GENERIC;
+  if (a.conv_kh > 0) {       // implicit-GEMM convolution: generic epilogue (folded BatchNorm scale / bias, residual, ReLU), one CTA per SM
+    if constexpr (OCC == 1) return launch_gemm<false, false, CG, NP, 1, EPI_GENERIC, true>(a, bn, splits, s);
+    else { vb_set_last_error("vb_gemm_bf16", "convolution kernels are built for one CTA per SM"); return VB_ERR_UNSUPPORTED; }
+  }
   if constexpr (CG == 2) {
     if (!a.a_mn_major && !a.b_mn_major) {
       if (epi == EPI_BIAS) return launch_gemm<false, false, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);
@@ -1025,6 +1111,17 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* args, void* stream) {
   VB_REQUIRE(a.a && a.b && a.d, "a, b and d must be non-null device pointers");
   VB_REQUIRE(a.m > 0 && a.n > 0 && a.k > 0, "m, n, k must be positive");
   VB_REQUIRE(a.n % 8 == 0, "n must be a multiple of 8");
+  if (a.conv_kh > 0) {
+    VB_REQUIRE(a.conv_kw > 0 && a.conv_stride > 0 && a.conv_pad >= 0 && a.conv_n > 0 && a.conv_h > 0 && a.conv_w > 0 && a.conv_c > 0,
+               "convolution geometry must be positive");
+    VB_REQUIRE(a.conv_c % 64 == 0, "implicit-GEMM convolution needs a multiple of 64 input channels");
+    VB_REQUIRE(!a.a_mn_major && !a.b_mn_major, "implicit-GEMM convolution takes an NHWC activation and a [Cout, kh*kw*Cin] weight");
+    VB_REQUIRE(a.conv_kh <= 16 && a.conv_kw <= 16 && a.conv_pad < 128 && a.conv_stride <= 8, "window / padding / stride out of the TMA im2col range");
+    const long long ho = (a.conv_h + 2 * a.conv_pad - a.conv_kh) / a.conv_stride + 1, wo = (a.conv_w + 2 * a.conv_pad - a.conv_kw) / a.conv_stride + 1;
+    VB_REQUIRE(ho > 0 && wo > 0 && a.m == (long long)a.conv_n * ho * wo && a.k == a.conv_kh * a.conv_kw * a.conv_c,
+               "m must be n*ho*wo and k must be kh*kw*c of the convolution");
+    VB_REQUIRE(a.splits <= 1 && !a.accumulate, "no split-K for convolutions");
+  }
   VB_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
   VB_REQUIRE((reinterpret_cast<uintptr_t>(a.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.b) & 15) == 0,
              "a/b must be 16-byte aligned");

@@ -28,32 +28,36 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 
 // ------------------------------------------------------------------------------------------------ stem im2col
 // y[(n*ho + oy)*wo + ox, (ky*kw + kx)*3 + c] = img[n, c, oy*stride - pad + ky, ox*stride - pad + kx]  (0 outside), columns
-// [kh*kw*3, kpad) are zero.  One thread per (pixel, ky): writes kw*3 contiguous values.
+// [kh*kw*3, kpad) are zero.  One thread per 16-byte piece (8 columns) of the output: the pieces of consecutive threads are
+// consecutive in memory (a row is kpad / 8 whole pieces), so every warp writes 512 contiguous bytes; the gathers hit L1 / L2
+// (every input value is used kh*kw / stride^2 ~ 12 times).  The first version (one thread per (pixel, ky), 2-byte stores)
+// ran at 0.36 TB/s: 1.2 ms of the 12.5 ms batch-16 pass.
 __global__ void stem_im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ y, int n, int h, int w,
                                    int ho, int wo, int kh, int kw, int stride, int pad, int kpad) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)n * ho * wo * (kh + 1);   // slot kh = the zero padding tail
-  if (idx >= total) return;
-  const int ky = (int)(idx % (kh + 1));
-  const long long pix = idx / (kh + 1);
-  const int ox = (int)(pix % wo);
-  const int oy = (int)((pix / wo) % ho);
-  const int b = (int)(pix / ((long long)wo * ho));
-  __nv_bfloat16* dst = y + pix * kpad;
-  if (ky == kh) {
-    for (int i = kh * kw * 3; i < kpad; ++i) dst[i] = __float2bfloat16_rn(0.f);
-    return;
-  }
-  const int iy = oy * stride - pad + ky;
-  dst += ky * kw * 3;
-  for (int kx = 0; kx < kw; ++kx) {
-    const int ix = ox * stride - pad + kx;
-    const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+  const int pieces = kpad >> 3;
+  const long long total = (long long)n * ho * wo * pieces;
+  const int kcols = kh * kw * 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % pieces);
+    const long long pix = idx / pieces;
+    const int ox = (int)(pix % wo);
+    const int oy = (int)((pix / wo) % ho);
+    const int b = (int)(pix / ((long long)wo * ho));
+    const float* src = img + (long long)b * 3 * h * w;
+    const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+    float v[8];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v = ok ? __ldg(img + (((long long)b * 3 + c) * h + iy) * w + ix) : 0.f;
-      dst[kx * 3 + c] = __float2bfloat16_rn(v);
+    for (int i = 0; i < 8; ++i) {
+      const int col = q * 8 + i;
+      const int tap = col / 3, c = col - tap * 3;
+      const int ky = tap / kw, kx = tap - ky * kw;
+      const int iy = iy0 + ky, ix = ix0 + kx;
+      const bool ok = col < kcols && iy >= 0 && iy < h && ix >= 0 && ix < w;
+      v[i] = ok ? __ldg(src + ((long long)c * h + iy) * w + ix) : 0.f;
     }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(y + idx * 8) = o;
   }
 }
 
@@ -279,9 +283,10 @@ extern "C" int vb_stem_im2col(const float* img, void* y, int32_t n, int32_t h, i
   VB_REQUIRE(kh > 0 && kw > 0 && stride > 0 && pad >= 0 && kpad >= kh * kw * 3 && kpad % 8 == 0, "bad window / kpad");
   const int ho = (h + 2 * pad - kh) / stride + 1, wo = (w + 2 * pad - kw) / stride + 1;
   VB_REQUIRE(ho > 0 && wo > 0, "empty output");
-  const long long total = (long long)n * ho * wo * (kh + 1);
-  stem_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)y, n, h, w, ho, wo,
-                                                                                     kh, kw, stride, pad, kpad);
+  VB_REQUIRE(al16(y), "output must be 16-byte aligned");
+  const long long total = (long long)n * ho * wo * (kpad / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)y, n, h, w, ho, wo, kh, kw,
+                                                                          stride, pad, kpad);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;
 }

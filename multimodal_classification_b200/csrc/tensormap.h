@@ -18,4 +18,10 @@ int make_tensor_map_2d_sw64(CUtensorMap* out, const void* base, int64_t inner, i
 // bf16, [d2, d1, d0] with element strides (s2, s1, 1); 128-byte swizzle.
 int make_tensor_map_3d(CUtensorMap* out, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t s1,
                        int64_t s2, int box0, int box1, int box2);
+// bf16 NHWC activation [n, h, w, c] read in IM2COL mode (cuTensorMapEncodeIm2col): one load fetches `pixels` consecutive output
+// pixels x 64 channels of ONE filter tap (the tap is the instruction's {kx, ky} offset operand) of a kh x kw / stride / pad
+// convolution, laid out in shared memory exactly like a K-major [pixels, 64] box with the 128-byte swizzle; input positions
+// outside the picture read as zeros.  c % 64 == 0.
+int make_tensor_map_im2col(CUtensorMap* out, const void* base, int n, int h, int w, int c, int kh, int kw, int stride,
+                           int pad, int pixels);
 }  // namespace vb

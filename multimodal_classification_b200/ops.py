@@ -29,8 +29,12 @@ def _need_cuda(*ts):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
          bias=None, scale=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, preact=None, accumulate=False,
-         block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False) -> torch.Tensor:
+         block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False, conv=None) -> torch.Tensor:
     """out[M,N] = epilogue(sum_k A(m,k) B(n,k)).
+
+    conv=(kh, kw, stride, pad): `a` is a contiguous NHWC bf16 activation [n, h, w, c] (c % 64 == 0) and the product is the
+    convolution with the weight b [N, kh*kw*c] (column (ky*kw + kx)*c + ci): out[n*ho*wo, N].  The A tiles are gathered by TMA in
+    im2col mode -- no [pixels, kh*kw*c] matrix is materialised (nn.Conv2d of the ResNet trunk, resnet152_roi.py:49-74).
 
     a: [M,K] (K-major) or [K,M] (a_mn_major); b: [N,K] or [K,N] (b_mn_major); bf16, last dim contiguous.
     out: bf16 or fp32 [M,N].  Mirrors nn.Linear forward / dgrad / wgrad
@@ -39,7 +43,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     _need_cuda(a, b, out, bias, scale, aux, preact)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     assert a.stride(-1) == 1 and b.stride(-1) == 1 and out.stride(-1) == 1
-    if a_mn_major:
+    cn = ch = cw = cc = ckh = ckw = cstride = cpad = 0
+    if conv is not None:
+        assert not a_mn_major and not b_mn_major and a.dim() == 4 and a.is_contiguous()
+        ckh, ckw, cstride, cpad = conv
+        cn, ch, cw, cc = a.shape
+        m = cn * ((ch + 2 * cpad - ckh) // cstride + 1) * ((cw + 2 * cpad - ckw) // cstride + 1)
+        k = ckh * ckw * cc
+    elif a_mn_major:
         k, m = a.shape
     else:
         m, k = a.shape
@@ -57,7 +68,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
         assert bias.dtype == torch.float32 and bias.numel() == n
     if scale is not None:
         assert scale.dtype == torch.float32 and scale.numel() == n
-    args.lda, args.ldb, args.ldd = a.stride(0), b.stride(0), out.stride(0)
+    args.lda, args.ldb, args.ldd = (0 if conv is not None else a.stride(0)), b.stride(0), out.stride(0)
+    args.conv_n, args.conv_h, args.conv_w, args.conv_c = cn, ch, cw, cc
+    args.conv_kh, args.conv_kw, args.conv_stride, args.conv_pad = ckh, ckw, cstride, cpad
     args.ld_preact = preact.stride(0) if preact is not None else 0
     args.ld_aux = aux.stride(0) if aux is not None else 0
     args.m, args.n, args.k = m, n, k

@@ -175,6 +175,10 @@ class _Trunk:
             self.layer4 = self._prep_layer(bb.top)
         self.arena: Dict[str, torch.Tensor] = {}
         self.arena_gen = 0
+        # 3x3 and strided convolutions as implicit GEMMs (TMA im2col loads).  VB_CONV_EXPLICIT=1: materialise the
+        # [pixels, kh*kw*Cin] matrix first (the round-1 path, kept for A/B measurements and as the kernel's own cross-check)
+        import os
+        self.implicit = os.environ.get("VB_CONV_EXPLICIT", "0") != "1"
 
     @staticmethod
     def _prep_layer(layer: nn.Sequential):
@@ -204,15 +208,18 @@ class _Trunk:
         assert cin == c.cin, (cin, c.cin)
         ho = (h + 2 * c.pad - c.kh) // c.stride + 1
         wo = (w + 2 * c.pad - c.kw) // c.stride + 1
+        conv = None
         if c.kh == 1 and c.kw == 1 and c.stride == 1:
             a = x.view(-1, cin)
+        elif self.implicit and cin % 64 == 0:
+            a, conv = x, (c.kh, c.kw, c.stride, c.pad)      # implicit GEMM: TMA gathers the filter taps (im2col mode)
         else:
             a = self.buf("col", (b * ho * wo, c.kh * c.kw * cin))
             ops.im2col_nhwc(x, a, c.kh, c.kw, c.stride, c.pad)
         out = self.buf(out_name, (b, ho, wo, c.cout))
         ops.gemm(a, c.w, out.view(-1, c.cout), scale=c.scale, bias=c.bias, act=ACT_RELU if relu else ACT_NONE,
                  aux=None if residual is None else residual.view(-1, c.cout),
-                 aux_mode=ops.AUX_NONE if residual is None else ops.AUX_ADD)
+                 aux_mode=ops.AUX_NONE if residual is None else ops.AUX_ADD, conv=conv)
         return out
 
     def bottleneck(self, x: torch.Tensor, blk, out_name: str):

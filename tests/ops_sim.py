@@ -22,7 +22,13 @@ def _no_dropout(*ps):
 
 
 def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, scale=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE,
-         preact=None, accumulate=False, block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False):
+         preact=None, accumulate=False, block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False, conv=None):
+    if conv is not None:                                          # implicit-GEMM convolution: a is the NHWC activation
+        kh, kw, stride, pad = conv
+        n, h, w, c = a.shape
+        ho, wo = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+        cols = F.unfold(a.float().permute(0, 3, 1, 2), (kh, kw), padding=pad, stride=stride)
+        a = cols.view(n, c, kh * kw, ho * wo).permute(0, 3, 2, 1).reshape(n * ho * wo, kh * kw * c)
     am = a.float().t() if a_mn_major else a.float()               # [M, K]
     bm = b.float().t() if b_mn_major else b.float()               # [N, K]
     v = am @ bm.t()

@@ -110,6 +110,46 @@ def test_pooling_and_im2col_kernels():
     assert torch.allclose(o.cpu(), y.float().mean(1), atol=1e-5)
 
 
+CONV_CASES = [  # (n, h, w, cin, cout, k, stride, pad): the trunk's 3x3s and strided 1x1s, odd sizes, one / two CTAs, ragged last tile
+    (2, 14, 14, 512, 512, 3, 2, 1), (1, 38, 38, 256, 256, 3, 1, 1), (2, 37, 29, 128, 128, 3, 1, 1), (1, 75, 75, 256, 512, 1, 2, 0),
+    (3, 7, 7, 512, 512, 3, 1, 1), (1, 6, 6, 256, 256, 3, 1, 1), (2, 150, 150, 64, 64, 3, 1, 1), (1, 75, 75, 128, 128, 3, 2, 1),
+    (36, 14, 14, 1024, 2048, 1, 2, 0), (5, 9, 11, 64, 1024, 3, 1, 1), (1, 38, 63, 1024, 512, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_implicit_gemm_convolution_equals_explicit_im2col(case):
+    """vb_gemm_bf16 in convolution mode (A gathered by TMA im2col loads from the NHWC activation) against the same GEMM over the
+    materialised [pixels, kh*kw*Cin] matrix: same tiles, same k order -> bit-identical; and against F.conv2d in fp32."""
+    from multimodal_classification_b200 import ops
+    n, h, w, cin, cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).cuda()
+    wt = (torch.randn(cout, k * k * cin, generator=g) / (k * k * cin) ** 0.5).to(torch.bfloat16).cuda()
+    scale, bias = (0.5 + torch.rand(cout, generator=g)).cuda(), torch.randn(cout, generator=g).cuda()
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    res = torch.randn(n * ho * wo, cout, generator=g).to(torch.bfloat16).cuda()
+    col = torch.empty(n * ho * wo, k * k * cin, dtype=torch.bfloat16, device="cuda")
+    ops.im2col_nhwc(x, col, k, k, stride, pad)
+    kw = dict(scale=scale, bias=bias, act=ops.ACT_RELU, aux=res, aux_mode=ops.AUX_ADD)
+    explicit = ops.gemm(col, wt, torch.empty(n * ho * wo, cout, dtype=torch.bfloat16, device="cuda"), **kw)
+    implicit = ops.gemm(x, wt, torch.full((n * ho * wo, cout), float("nan"), dtype=torch.bfloat16, device="cuda"), conv=(k, k, stride, pad), **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(implicit, explicit), float((implicit.float() - explicit.float()).abs().max())
+    w4 = wt.float().view(cout, k, k, cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4, stride=stride, padding=pad) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
+    ref = F.relu(ref.permute(0, 2, 3, 1).reshape(n * ho * wo, cout) + res.float())
+    assert float((implicit.float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
+def test_convolution_mode_rejects_bad_geometry():
+    from multimodal_classification_b200 import ops
+    from multimodal_classification_b200._lib import VbError
+    x = torch.zeros(1, 8, 8, 32, dtype=torch.bfloat16, device="cuda")           # 32 channels: not a multiple of 64
+    wt = torch.zeros(64, 9 * 32, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(VbError):
+        ops.gemm(x, wt, torch.empty(64, 64, dtype=torch.bfloat16, device="cuda"), conv=(3, 3, 1, 1))
+
+
 @pytest.fixture(scope="module")
 def extractor():
     from multimodal_classification_b200.resnet152_roi import ResNet152ROIExtractor
