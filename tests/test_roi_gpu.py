@@ -96,13 +96,14 @@ def test_pooling_and_im2col_kernels():
         ref = ref.view(2, 16, k * k, ho * wo).permute(0, 3, 2, 1).reshape(2 * ho * wo, k * k * 16)
         assert torch.equal(col.float().cpu(), ref)
     # stem im2col: fp32 NCHW image -> bf16 [pixels, 152]
-    img = torch.randn(2, 3, 30, 22, generator=g)
-    ho, wo = (30 + 6 - 7) // 2 + 1, (22 + 6 - 7) // 2 + 1
-    col = torch.full((2 * ho * wo, 152), 9.0, dtype=torch.bfloat16, device="cuda")
-    ops.stem_im2col(img.cuda(), col)
-    ref = F.unfold(img, 7, padding=3, stride=2).view(2, 3, 49, ho * wo).permute(0, 3, 2, 1).reshape(2 * ho * wo, 147)
-    assert torch.equal(col[:, :147].float().cpu(), ref.to(torch.bfloat16).float())
-    assert col[:, 147:].abs().max().item() == 0
+    for ih, iw in ((30, 22), (21, 301), (9, 128)):                          # one segment / several with a ragged last one / exact
+        img = torch.randn(2, 3, ih, iw, generator=g)
+        ho, wo = (ih + 6 - 7) // 2 + 1, (iw + 6 - 7) // 2 + 1
+        col = torch.full((2 * ho * wo, 152), 9.0, dtype=torch.bfloat16, device="cuda")
+        ops.stem_im2col(img.cuda(), col)
+        ref = F.unfold(img, 7, padding=3, stride=2).view(2, 3, 49, ho * wo).permute(0, 3, 2, 1).reshape(2 * ho * wo, 147)
+        assert torch.equal(col[:, :147].float().cpu(), ref.to(torch.bfloat16).float()), (ih, iw)
+        assert col[:, 147:].abs().max().item() == 0
     # global average pool
     y = torch.randn(5, 49, 64, generator=g).to(torch.bfloat16)
     o = torch.empty(5, 64, device="cuda")

@@ -24,11 +24,13 @@ def main():
     ext.extract_batch(imgs)                     # eager + capture
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()                 # ncu --profile-from-start off: only the replays are profiled
     s.record()
     for _ in range(args.replays):
         feats, _ = ext.extract_batch(imgs)
     e.record()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     print(f"{size}x{size} {mode}-{roi} batch {args.batch}: {s.elapsed_time(e) / args.replays:.3f} ms per replay, finite {bool(torch.isfinite(feats).all())}")
 
 
