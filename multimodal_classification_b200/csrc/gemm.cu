@@ -12,7 +12,7 @@
 // (any multiple of 32 up to 256: UMMA N is free in steps of 16) picked per problem so that the pair tiles fill the 74 TPCs
 // in as few waves as possible.  CG = 1 (single CTA, M = 128) remains for one-row-block problems (poolers, classifier).
 //
-// Round-2 structure (what the in-kernel clock64 timeline of round 1 asked for, profiles/r02a_gemm_timeline.md):
+// Round-2 structure (what the in-kernel clock64 timeline of round 1 asked for; the round-2 timeline is profiles/r02_gemm_timeline.txt):
 //   * prologue: every thread arrives on the cluster barrier at entry; barrier init, TMEM allocation and descriptor prefetch
 //     run in parallel behind it, and the producer issues its first loads as soon as the barrier and griddepcontrol.wait
 //     return (first load ~1800 -> ~700 cycles after entry).
@@ -26,6 +26,14 @@
 // MN-major (descriptor + TMA box change only), so forward, dgrad and wgrad of nn.Linear (reference
 // models/vilbert_facebook_arch.py:127-129 etc.) all run here without a transposed copy of anything.  The kernel is
 // launched with programmatic dependent launch.  See include/vilbert_b200.h for the ABI.
+//
+// CONV kernels (implicit-GEMM convolution, the 3x3 and strided 1x1 layers of the ResNet trunks): the A operand is the NHWC
+// activation itself, described by an IM2COL tensor map (cuTensorMapEncodeIm2col).  A k-block is one filter tap x 64 input
+// channels; the producer decodes the tile's first output pixel once per tile, steps (channel block, kx, ky) counters per
+// k-block and issues cp.async.bulk.tensor.4d...im2col with the tap as the instruction's offset operand.  The bytes land in
+// shared memory exactly as a K-major [128 pixels, 64] box would (zero padding = out-of-bounds fill), so the MMA issuer, the
+// multicast halves and the epilogue are untouched and the result is bit-identical to the GEMM over a materialised
+// [pixels, kh*kw*Cin] matrix -- which no longer exists (it was 38 % of the RoI stage's kernel time, profiles/r02_roi_stage.md).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -851,7 +859,7 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   int rc;
   // K-major operand: global [rows, K] -> box {64 (k), rows_per_cta}; MN-major: global [K, rows] -> box {64 (mn), 64 (k)}
   // (Tried: describing an MN-major operand as a 3-D tensor (64 | k | piece) so that ONE instruction fetches every 64-wide piece
-  // of a tile.  Measured slower on B200 -- weight gradients 1 031 -> 1 270 us per step, profiles/r02_gemm_experiments.md -- and
+  // of a tile.  Measured slower on B200 -- weight gradients 1 031 -> 1 270 us per step, profiles/r02_gemm_experiments.md (gpurun_out/r02v_*) -- and
   // removed: one 2-D load per piece.)
   if (CONV)      rc = make_tensor_map_im2col(&map_a, a.a, a.conv_n, a.conv_h, a.conv_w, a.conv_c, a.conv_kh, a.conv_kw, a.conv_stride,
                                              a.conv_pad, GEMM_BM / NP);
