@@ -151,7 +151,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "vilbert_base_train_step_bs16_t128_r100", "per_gpu_batch": bs, "tokens": T, "regions": R},
+            "config": {"workload": "vilbert_base_train_step_bs16_t128_r100", "per_gpu_batch": bs, "global_batch": bs, "tokens": T,
+                       "regions": R, "dropout": False, "step": "fwd+bwd (fp32 autograd on the host cores)", "parallelism": "cpu",
+                       "grad_exchange": "none", "l2": "n/a (CPU)", "cuda_graphs": False},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
