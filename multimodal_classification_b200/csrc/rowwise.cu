@@ -458,12 +458,14 @@ __global__ void cast_multi_kernel(const CastSeg* segs, const int* block_seg, con
   }
 }
 
+// The fp32 source is read ONCE per step (ld.global.cs = evict-first): the refresh runs beside the first layers of the forward,
+// whose activations live in L2.
 __global__ void cast_kernel(const float* src, __nv_bfloat16* dst, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
-      float v[8];
-      ld8f(src + i, v);
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(src + i)), b = __ldcs(reinterpret_cast<const float4*>(src + i + 4));
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
       st8(dst + i, v);
     } else {
       for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16_rn(src[k]);
@@ -846,7 +848,8 @@ extern "C" int vb_colsum_bf16(const void* x, int64_t ld, int32_t m, int32_t n, f
 extern "C" int vb_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   VB_REQUIRE(src && dst && n > 0 && aligned16(src) && aligned16(dst), "bad cast arguments");
   long long blocks = (n + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  static const int cap = getenv("VB_CAST_BLOCKS") ? atoi(getenv("VB_CAST_BLOCKS")) : 148 * 16;
+  if (blocks > cap) blocks = cap;
   cast_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;

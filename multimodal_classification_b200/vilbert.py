@@ -258,6 +258,7 @@ class _FlatParams:
         # gradient buckets for data-parallel training: one per encoder block, in flat-buffer order
         from . import ddp
         groups: Dict[str, List[str]] = {}
+        self.block_of: Dict[str, str] = {}      # GEMM weight -> the block (= gradient bucket = shadow-refresh unit) holding it
         for k in order_w:
             parts = k.split(".")
             if parts[1] == "encoder":
@@ -265,6 +266,7 @@ class _FlatParams:
             else:
                 name = "tail"
             groups.setdefault(name, []).append(k)
+            self.block_of[k] = name
         self.buckets = ddp.block_ranges(self.offsets, {k: named[k].numel() for k in named}, list(groups.items()), self.s_end)
 
     # fused q|k|v biases are laid out back to back: check rather than assume
@@ -331,6 +333,7 @@ class _Plan:
         self.twins: Dict[int, torch.Tensor] = {}     # bf16 activation (data_ptr) -> its fp32 twin (residual stream)
         self.ring: Dict[Any, int] = {}               # LayerNorms issued so far per activation shape (fp32 ring index)
         self.fwd_graph = None
+        self.fwd_graph_r = None        # the forward graph that carries the bf16 shadow refresh
         self.bwd_graph = None
         self.fwd_runs = 0
         self.bwd_runs = 0
@@ -426,6 +429,14 @@ class _Engine:
         self.strict_inputs = os.environ.get("VB_STRICT_INPUTS", "0") == "1"
         self.refresh_stream = (torch.cuda.Stream(device=device)
                                if torch.device(device).type == "cuda" and os.environ.get("VB_SYNC_REFRESH", "0") != "1" else None)
+        # The bf16 shadow refresh as a branch of the FORWARD graph: block by block in execution order on the refresh stream, every
+        # GEMM waiting only for its own block's cast -- 1.5 GB of HBM streaming beside the first layers' compute instead of 0.19 ms
+        # in front of them.  VB_REFRESH_IN_GRAPH=0: one cast before the forward (round-2 baseline, A/B runs).
+        self.refresh_in_graph = self.refresh_stream is not None and os.environ.get("VB_REFRESH_IN_GRAPH", "1") != "0"
+        self.refresh_pending = False          # set by _ensure_engine: the next forward carries the refresh
+        self._refresh_events: Optional[Dict[str, Any]] = None
+        self._refresh_waited = set()
+        self._refresh_now = False
         self.grads_clean = False     # set by ViLBERTForClassification.zero_grad(set_to_none=False)
         self.comm_group = getattr(model, "_ddp_group", None)   # data-parallel: see ddp.attach()
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1) if self.comm_group is not None else None   # as urgent as the chain: NCCL CTAs must get SM slots while GEMMs are running
@@ -459,9 +470,53 @@ class _Engine:
                 f.check_contiguous([f"{p}.query{s}.bias", f"{p}.key{s}.bias", f"{p}.value{s}.bias"])
 
     # ------------------------------------------------------------------------------------------------ primitives
+    def _shadow(self, wkey, rows=None):
+        """bf16 shadow of a GEMM weight for a FORWARD kernel on the current stream; during a refreshing forward the stream first
+        waits (once per block) for the cast of the block that holds it."""
+        if self._refresh_events is not None:
+            block = self.flat.block_of[wkey]
+            cur = torch.cuda.current_stream()
+            mark = (cur.cuda_stream, block)
+            if mark not in self._refresh_waited:
+                cur.wait_event(self._refresh_events[block])
+                self._refresh_waited.add(mark)
+        return self.flat.w(wkey, rows)
+
+    def _refresh_order(self) -> List[str]:
+        """Blocks in the order the forward first touches them (run_forward)."""
+        cfg = self.cfg
+        order, c = ["tail", "t0"], 0
+        if cfg["v_num_hidden_layers"] > 0:
+            order.append("v0")              # the visual stream starts its first layer beside the first text layer
+        for i in range(cfg["num_hidden_layers"]):
+            order.append(f"t{i}")
+            if i in CO_ATTENTION_TEXT_LAYERS and c < cfg["num_co_attention_layers"]:
+                order += [f"v{c}", f"c{c}", f"v{c + 1}"]
+                c += 1
+        seen, out = set(), []
+        for n in order + list(self.flat.buckets):
+            if n in self.flat.buckets and n not in seen:
+                seen.add(n)
+                out.append(n)
+        return out
+
+    def _begin_refresh(self, s_t) -> None:
+        f, rs = self.flat, self.refresh_stream
+        rs.wait_stream(s_t)
+        self._refresh_events, self._refresh_waited = {}, set()
+        with torch.cuda.stream(rs):
+            for name in self._refresh_order():
+                lo, hi = f.buckets[name]
+                hi = min(hi, f.w_end)
+                if hi > lo:
+                    ops.cast_bf16(f.master[lo:hi], f.shadow[lo:hi])
+                ev = torch.cuda.Event()
+                ev.record(rs)
+                self._refresh_events[name] = ev
+
     def _linear(self, x, wkey, out, *, rows=None, act=ops.ACT_NONE, preact=None):
         f = self.flat
-        w = f.w(wkey, rows)
+        w = self._shadow(wkey, rows)
         bkey = wkey[:-len("weight")] + "bias"
         ops.gemm(x, w, out, bias=f.m(bkey, w.shape[0]), act=act, preact=preact, b_streamed=True)
 
@@ -664,6 +719,8 @@ class _Engine:
         pl.twins.clear()
         if pl.dropout:
             ops.seed_advance(self.seed, pl.seed)
+        if self._refresh_now:
+            self._begin_refresh(s_t)
         s_v.wait_stream(s_t)
 
         # text embeddings (transformers BertEmbeddings) | visual embeddings (reference :100-104)
@@ -688,7 +745,7 @@ class _Engine:
                               f.m(ve + ".image_location_embeddings.bias"), loc)
             if pl.onehot_r is not None:     # + position_embeddings[region]  (vilbert_core.py:470-476)
                 res = pl.buf("vemb.res", (Mv, Hv))
-                ops.gemm(pl.onehot_r[:, :R], f.w(V_POS_KEY)[:R], res, b_mn_major=True, aux=loc, aux_mode=ops.AUX_ADD)
+                ops.gemm(pl.onehot_r[:, :R], self._shadow(V_POS_KEY)[:R], res, b_mn_major=True, aux=loc, aux_mode=ops.AUX_ADD)
                 loc = res
             v = pl.buf("vemb.v", (Mv, Hv))
             sv["vemb_ln"] = self._ln(pl, img, loc, ve + ".LayerNorm", v, "vemb.ln", p_out=pvh)
@@ -708,7 +765,7 @@ class _Engine:
 
         # poolers (:404-408), concat, classifier (:569-578), CE (:637-639)
         pooled = pl.buf("head.pooled", (B, bi + Hv))
-        ops.gemm(t.view(B, T * H)[:, :H], f.w("bert.t_pooler.dense.weight"), pooled[:, :bi],
+        ops.gemm(t.view(B, T * H)[:, :H], self._shadow("bert.t_pooler.dense.weight"), pooled[:, :bi],
                  bias=f.m("bert.t_pooler.dense.bias"), act=ops.ACT_TANH)
         if pl.onehot_b is not None:         # mean over the regions (vilbert_core.py:581) instead of the first region (:404-408)
             vmean32 = pl.buf("head.vmean32", (B, Hv), torch.float32)
@@ -716,7 +773,7 @@ class _Engine:
             v_in = ops.cast_bf16(vmean32, pl.buf("head.vmean", (B, Hv)))
         else:
             v_in = v.view(B, R * Hv)[:, :Hv]
-        ops.gemm(v_in, f.w("bert.v_pooler.dense.weight"), pooled[:, bi:],
+        ops.gemm(v_in, self._shadow("bert.v_pooler.dense.weight"), pooled[:, bi:],
                  bias=f.m("bert.v_pooler.dense.bias"), act=ops.ACT_TANH)
         sv["head_site"] = self._next_site()
         pc = cfg.get("_classifier_dropout", 0.1)
@@ -724,13 +781,16 @@ class _Engine:
         if pl.dropout:
             pooled_d = ops.dropout(pooled, pl.buf("head.pooled_d", (B, bi + Hv)), pc, sv["head_site"], pl.seed)
         hid = pl.buf("head.hid", (B, bi))
-        ops.gemm(pooled_d, f.w("classifier.1.weight"), hid, bias=f.m("classifier.1.bias"), act=ops.ACT_RELU)
+        ops.gemm(pooled_d, self._shadow("classifier.1.weight"), hid, bias=f.m("classifier.1.bias"), act=ops.ACT_RELU)
         hid_d = hid
         if pl.dropout:
             hid_d = ops.dropout(hid, pl.buf("head.hid_d", (B, bi)), pc, sv["head_site"] + 1, pl.seed)
         ops.cls_ce_fwd(hid_d, f.m("classifier.4.weight").view(pl.C, bi), f.m("classifier.4.bias"), pl.labels, pl.logits,
                        pl.probs, pl.loss)
         sv.update(t_final=t, v_final=v, v_pool_in=v_in, pooled=pooled, pooled_d=pooled_d, hid=hid, hid_d=hid_d)
+        if self._refresh_events is not None:
+            s_t.wait_stream(self.refresh_stream)        # join the branch (every block was waited for long ago)
+            self._refresh_events = None
 
     def _co_layer_fwd(self, pl, c, v, t, s_t, s_v):
         """CoAttentionLayer.forward (reference :377-394): BiAttention :253-294, BiOutput :324-338, two FFNs."""
@@ -964,11 +1024,15 @@ class _Engine:
     def _execute(self, pl: _Plan, which: str):
         fn = self.run_forward if which == "fwd" else self.run_backward
         runs = pl.fwd_runs if which == "fwd" else pl.bwd_runs
-        graph = pl.fwd_graph if which == "fwd" else pl.bwd_graph
         if which == "fwd":
+            # a forward that carries the shadow refresh is a graph of its own (the refresh branch + one event wait per block)
+            self._refresh_now, self.refresh_pending = self.refresh_pending, False
+            slot = "fwd_graph_r" if self._refresh_now else "fwd_graph"
             pl.fwd_runs += 1
         else:
+            slot = "bwd_graph"
             pl.bwd_runs += 1
+        graph = getattr(pl, slot)
         caller = torch.cuda.current_stream()
         pl.s_main.wait_stream(caller)
         if not self.use_graphs or runs == 0:
@@ -983,10 +1047,7 @@ class _Engine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=pl.s_main, capture_error_mode="thread_local"):
                 fn(pl)
-            if which == "fwd":
-                pl.fwd_graph = graph
-            else:
-                pl.bwd_graph = graph
+            setattr(pl, slot, graph)
         with torch.cuda.stream(pl.s_main):
             graph.replay()
         caller.wait_stream(pl.s_main)
@@ -1132,7 +1193,9 @@ class ViLBERTForClassification(nn.Module):
         ver = eng.flat.versions()
         if ver != eng.flat._version:
             upd = eng.flat._updated
-            if upd is not None and upd[1] == ver and eng.refresh_stream is not None:
+            if eng.refresh_in_graph:
+                eng.refresh_pending = True        # the forward about to run casts the shadows block by block beside its first layers
+            elif upd is not None and upd[1] == ver and eng.refresh_stream is not None:
                 # nothing touched the parameters after the optimizer's hook: refresh beside whatever was queued since
                 # (the next batch's host-to-device copy), the forward waits for it below
                 eng.refresh_stream.wait_event(upd[0])
