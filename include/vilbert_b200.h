@@ -341,11 +341,35 @@ int vb_nms(const float* boxes, const float* scores, int32_t n, double iou_thresh
  *                       [regions,4], spatial fp32 [regions,5] = (x1/img_w, y1/img_h, x2/img_w, y2/img_h clamped to [0,1],
  *                       area) bit-exact with the reference's fp32 tensor ops, index int32 [regions], and feat_dst fp32
  *                       [regions, feat_dim] = rows of feat_src [n, feat_dim], rois fp32 [regions,5] = (batch_index, box): the
- *                       vb_roi_pool_nhwc operand of the chosen boxes.  *num_keep == 0 leaves the outputs untouched. */
+ *                       vb_roi_pool_nhwc operand of the chosen boxes.  *num_keep == 0 leaves the outputs untouched.  box_div:
+ *                       the boxes are divided by it (fp32, one rounding) before they are normalised -- the resize factor of
+ *                       fasterrcnn_vg_rpn.py:432 (``boxes / scale``); 1.0 is exact. */
 int vb_rowmax_f32(const float* x, int32_t rows, int32_t ld, int32_t col_begin, int32_t col_end, float* out, void* stream);
 int vb_select_regions(const float* candidates, const int32_t* keep, const int32_t* num_keep, int32_t regions, float img_w,
                       float img_h, const float* feat_src, int32_t feat_dim, float* boxes, float* spatial, float* feat_dst,
-                      int32_t* index, float* rois, float batch_index, void* stream);
+                      int32_t* index, float* rois, float batch_index, float box_div, void* stream);
+
+/* RPN-proposal variant of the Visual Genome extractor (models/feature_extractors/fasterrcnn_vg_rpn.py), post-processing on the
+ * device with no host read between the steps (counts stay in device memory):
+ *   vb_rpn_decode     : RPN.forward after the convolutions (:78-104) + _generate_anchors / _apply_deltas (:106-174) +
+ *                       clip_boxes_to_image + the min-size test of _filter_proposals (:444-450).  heads fp32 [fh*fw, ld]: columns
+ *                       [0, 2A) objectness logits (anchor k: 2k = background, 2k+1 = foreground), [2A, 6A) box deltas (4 per
+ *                       anchor); base_anchors = HOST array [A,4] (A <= 16).  boxes fp32 [fh*fw*A, 4] (anchor fastest), scores
+ *                       = softmax foreground probability, -inf where the clipped box is below min_size; *num_valid = the rest.
+ *   vb_rank_sort_desc : order[rank] = i, stable descending (torch.sort(descending=True, stable=True)); elements at or beyond
+ *                       *limit (optional device int) count as -inf.  The reference's torch.topk (:428, :455-458) is its prefix;
+ *                       among exactly tied scores topk's order is unspecified and the stable one is kept.
+ *   vb_gather_sorted  : the first min(cap, *num_valid) boxes / scores in that order (rows beyond: zero box, -inf); *count.
+ *   vb_nms_sorted     : torchvision.ops.nms over boxes ALREADY in descending score order (:461), stopping at max_keep survivors
+ *                       (:464-465); keep int32 [max_keep] = positions, *num_keep.  *count <= 8192. */
+int vb_rpn_decode(const float* heads, int32_t ld, int32_t fh, int32_t fw, int32_t num_anchors, const float* base_anchors,
+                  float stride, float img_h, float img_w, float min_size, float* boxes, float* scores, int32_t* num_valid,
+                  void* stream);
+int vb_rank_sort_desc(const float* scores, int32_t n, const int32_t* limit, int32_t* order, void* stream);
+int vb_gather_sorted(const float* boxes, const float* scores, const int32_t* order, const int32_t* num_valid, int32_t cap,
+                     float* out_boxes, float* out_scores, int32_t* count, void* stream);
+int vb_nms_sorted(const float* boxes, const int32_t* count, double iou_threshold, int32_t max_keep, int32_t* keep,
+                  int32_t* num_keep, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DINOv2 multi-layer fusion tail (next-row f-2; models/feature_extractors/dinov2_multilayer.py:342-381).

@@ -156,7 +156,11 @@ def _declare(l: C.CDLL) -> None:
         "vb_box_area_score": [vp, i32, f32, f32, f32, vp, vp],
         "vb_nms": [vp, vp, i32, C.c_double, vp, vp, vp, vp],
         "vb_rowmax_f32": [vp, i32, i32, i32, i32, vp, vp],
-        "vb_select_regions": [vp, vp, vp, i32, f32, f32, vp, i32, vp, vp, vp, vp, vp, f32, vp],
+        "vb_select_regions": [vp, vp, vp, i32, f32, f32, vp, i32, vp, vp, vp, vp, vp, f32, f32, vp],
+        "vb_rpn_decode": [vp, i32, i32, i32, i32, vp, f32, f32, f32, f32, vp, vp, vp, vp],
+        "vb_rank_sort_desc": [vp, i32, vp, vp, vp],
+        "vb_gather_sorted": [vp, vp, vp, vp, i32, vp, vp, vp, vp],
+        "vb_nms_sorted": [vp, vp, C.c_double, i32, vp, vp, vp],
         "vb_lmdb_regions": [vp, vp, i64, vp, vp, i32, i32, f32, f32, vp],
         "vb_attn_merge": [vp, vp, i32, i64, vp, i64, vp, i32, i32, i32, i64, i32, vp],
         "vb_attn_delta": [vp, i64, vp, i64, vp, i32, i32, i32, i64, i32, vp],

@@ -87,7 +87,7 @@ __global__ void select_regions_kernel(const float* __restrict__ cand, const int*
                                       const int* __restrict__ num_keep, float img_w, float img_h,
                                       const float* __restrict__ feat_src, int feat_dim, float* __restrict__ boxes,
                                       float* __restrict__ spatial, float* __restrict__ feat_dst, int* __restrict__ index,
-                                      float* __restrict__ rois, float batch_index) {
+                                      float* __restrict__ rois, float batch_index, float box_div) {
   const int r = blockIdx.x;
   const int nk = *num_keep;
   if (nk <= 0) return;
@@ -101,8 +101,10 @@ __global__ void select_regions_kernel(const float* __restrict__ cand, const int*
       q[0] = batch_index; q[1] = b.x; q[2] = b.y; q[3] = b.z; q[4] = b.w;
     }
     if (spatial) {
-      const float x1 = fminf(fmaxf(__fdiv_rn(b.x, img_w), 0.0f), 1.0f), y1 = fminf(fmaxf(__fdiv_rn(b.y, img_h), 0.0f), 1.0f);
-      const float x2 = fminf(fmaxf(__fdiv_rn(b.z, img_w), 0.0f), 1.0f), y2 = fminf(fmaxf(__fdiv_rn(b.w, img_h), 0.0f), 1.0f);
+      const float x1 = fminf(fmaxf(__fdiv_rn(__fdiv_rn(b.x, box_div), img_w), 0.0f), 1.0f);
+      const float y1 = fminf(fmaxf(__fdiv_rn(__fdiv_rn(b.y, box_div), img_h), 0.0f), 1.0f);
+      const float x2 = fminf(fmaxf(__fdiv_rn(__fdiv_rn(b.z, box_div), img_w), 0.0f), 1.0f);
+      const float y2 = fminf(fmaxf(__fdiv_rn(__fdiv_rn(b.w, box_div), img_h), 0.0f), 1.0f);
       float* s = spatial + 5 * r;
       s[0] = x1; s[1] = y1; s[2] = x2; s[3] = y2;
       s[4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
@@ -151,7 +153,8 @@ extern "C" int vb_rowmax_f32(const float* x, int32_t rows, int32_t ld, int32_t c
 extern "C" int vb_select_regions(const float* candidates, const int32_t* keep, const int32_t* num_keep, int32_t regions,
                                  float img_w, float img_h, const float* feat_src, int32_t feat_dim, float* boxes,
                                  float* spatial, float* feat_dst, int32_t* index, float* rois, float batch_index,
-                                 void* stream) {
+                                 float box_div, void* stream) {
+  VB_REQUIRE(box_div > 0.f, "box_div must be positive");
   VB_REQUIRE(candidates && keep && num_keep && regions >= 0, "null pointer");
   VB_REQUIRE((reinterpret_cast<uintptr_t>(candidates) & 15) == 0 && (reinterpret_cast<uintptr_t>(boxes) & 15) == 0,
              "boxes must be 16-byte aligned");
@@ -162,7 +165,7 @@ extern "C" int vb_select_regions(const float* candidates, const int32_t* keep, c
   if (regions == 0) return VB_OK;
   vb::select_regions_kernel<<<regions, 128, 0, static_cast<cudaStream_t>(stream)>>>(candidates, keep, num_keep, img_w, img_h,
                                                                                    feat_src, feat_dim, boxes, spatial,
-                                                                                   feat_dst, index, rois, batch_index);
+                                                                                   feat_dst, index, rois, batch_index, box_div);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;
 }

@@ -18,6 +18,7 @@ def install(ingest: bool = True) -> None:
     from .resnet152_roi import ResNet152ROIExtractor
     from .resnet_grid import ResNetFeatureExtractor, ResNetVGExtractor
     from .fasterrcnn_vg import FasterRCNNVGExtractor
+    from .fasterrcnn_vg_rpn import FasterRCNNVGRPNExtractor
     from .vilbert import ViLBERTForClassification, get_facebook_vilbert_config, load_facebook_weights
     from . import vilbert_core as core
 
@@ -39,6 +40,8 @@ def install(ingest: bool = True) -> None:
     B.FEATURE_EXTRACTOR_REGISTRY["resnet_vg"] = ResNetVGExtractor
     FE.FasterRCNNVGExtractor = FasterRCNNVGExtractor                   # "fasterrcnn_vg" (fasterrcnn_vg.py:170)
     B.FEATURE_EXTRACTOR_REGISTRY["fasterrcnn_vg"] = FasterRCNNVGExtractor
+    FE.FasterRCNNVGRPNExtractor = FasterRCNNVGRPNExtractor             # "fasterrcnn_vg_rpn" (fasterrcnn_vg_rpn.py:290)
+    B.FEATURE_EXTRACTOR_REGISTRY["fasterrcnn_vg_rpn"] = FasterRCNNVGRPNExtractor
     if ingest:
         from . import ingest as I
         for module, name in (("lmdb_dataset", "create_lmdb_dataloaders"), ("precomputed_dataset", "create_precomputed_dataloaders")):

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
+
 import torch
 
 from . import _lib
@@ -598,7 +600,7 @@ def rowmax(x, out, col_begin=0, col_end=None):
 
 
 def select_regions(candidates, keep, num_keep, regions, img_w, img_h, *, boxes=None, spatial=None, index=None, feat_src=None,
-                   feat_dst=None, rois=None, batch_index=0):
+                   feat_dst=None, rois=None, batch_index=0, box_div=1.0):
     """Region r <- candidate keep[min(r, num_keep - 1)]: box, normalised spatial row, feature row (fasterrcnn_vg.py:367-469)."""
     _need_cuda(candidates, keep, num_keep, boxes, spatial, index, feat_src, feat_dst, rois)
     assert candidates.dtype == torch.float32 and candidates.is_contiguous() and keep.dtype == torch.int32
@@ -612,7 +614,48 @@ def select_regions(candidates, keep, num_keep, regions, img_w, img_h, *, boxes=N
         assert feat_dst.is_contiguous() and tuple(feat_dst.shape) == (regions, dim)
     _lib.check(_lib.lib().vb_select_regions(candidates.data_ptr(), keep.data_ptr(), num_keep.data_ptr(), regions, float(img_w),
                                             float(img_h), _ptr(feat_src), dim, _ptr(boxes), _ptr(spatial), _ptr(feat_dst),
-                                            _ptr(index), _ptr(rois), float(batch_index), _stream()), "vb_select_regions")
+                                            _ptr(index), _ptr(rois), float(batch_index), float(box_div), _stream()),
+               "vb_select_regions")
+
+
+def rpn_decode(heads, fh, fw, base_anchors, stride, img_h, img_w, min_size, boxes, scores, num_valid):
+    """RPN head outputs -> clipped proposals + foreground scores (-inf below min_size) + their count (fasterrcnn_vg_rpn.py:78-174,
+    444-450).  heads fp32 [fh*fw, >= 6A]; base_anchors: HOST float32 array [A, 4]."""
+    _need_cuda(heads, boxes, scores, num_valid)
+    a = base_anchors.shape[0]
+    assert heads.dtype == torch.float32 and heads.stride(1) == 1 and heads.shape[0] == fh * fw
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and tuple(boxes.shape) == (fh * fw * a, 4)
+    assert scores.dtype == torch.float32 and scores.numel() == fh * fw * a and num_valid.dtype == torch.int32
+    host = np.ascontiguousarray(base_anchors, dtype=np.float32)
+    _lib.check(_lib.lib().vb_rpn_decode(heads.data_ptr(), heads.stride(0), fh, fw, a, host.ctypes.data, float(stride), float(img_h),
+                                        float(img_w), float(min_size), boxes.data_ptr(), scores.data_ptr(), num_valid.data_ptr(),
+                                        _stream()), "vb_rpn_decode")
+
+
+def rank_sort_desc(scores, order, limit=None):
+    """order[rank] = index, stable descending; elements at or beyond *limit (device int32) count as -inf."""
+    _need_cuda(scores, order, limit)
+    assert scores.dtype == torch.float32 and scores.is_contiguous() and order.dtype == torch.int32 and order.numel() >= scores.numel()
+    _lib.check(_lib.lib().vb_rank_sort_desc(scores.data_ptr(), scores.numel(), _ptr(limit), order.data_ptr(), _stream()),
+               "vb_rank_sort_desc")
+    return order
+
+
+def gather_sorted(boxes, scores, order, num_valid, out_boxes, out_scores, count):
+    """The first min(cap, *num_valid) boxes / scores in `order` (cap = rows of out_boxes)."""
+    _need_cuda(boxes, scores, order, num_valid, out_boxes, out_scores, count)
+    cap = out_boxes.shape[0]
+    assert out_boxes.dtype == torch.float32 and out_boxes.is_contiguous() and out_scores.numel() == cap and count.dtype == torch.int32
+    _lib.check(_lib.lib().vb_gather_sorted(boxes.data_ptr(), scores.data_ptr(), order.data_ptr(), num_valid.data_ptr(), cap,
+                                           out_boxes.data_ptr(), out_scores.data_ptr(), count.data_ptr(), _stream()), "vb_gather_sorted")
+
+
+def nms_sorted(boxes, count, iou_threshold, keep, num_keep):
+    """torchvision.ops.nms over boxes already in descending score order, first keep.numel() survivors (device counts)."""
+    _need_cuda(boxes, count, keep, num_keep)
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.shape[0] <= 8192 and keep.dtype == torch.int32
+    _lib.check(_lib.lib().vb_nms_sorted(boxes.data_ptr(), count.data_ptr(), float(iou_threshold), keep.numel(), keep.data_ptr(),
+                                        num_keep.data_ptr(), _stream()), "vb_nms_sorted")
 
 
 def lmdb_regions(features=None, features_bf16=None, boxes=None, spatial=None, box_div=1000.0, area_div=1000000.0, stream=None):

@@ -406,3 +406,125 @@ def vg_extract_features(sd, heads, img: torch.Tensor, num_regions: int = 36, nms
     with torch.no_grad():
         feats = forward_top(sd, torch.from_numpy(roi_pool(fmap.numpy(), rois, 14, 1.0 / 16.0))).numpy()
     return feats, normalize_boxes(boxes, w, h), boxes, scores
+
+
+# ------------------------------------------------------------------------------------------------ VG Faster R-CNN with RPN proposals (f-4)
+RPN_SCALES, RPN_RATIOS, RPN_STRIDE = (4, 8, 16, 32), (0.5, 1.0, 2.0), 16
+
+
+def seeded_rpn_state(seed: int = 13) -> Dict[str, torch.Tensor]:
+    """Seeded stand-ins for the Visual Genome checkpoint's ``RCNN_rpn`` tensors (fasterrcnn_vg_rpn.py:34-56); the box deltas are
+    kept small so that proposals stay anchor-like and many of them pass the min-size filter."""
+    g = torch.Generator().manual_seed(seed)
+    return {"RCNN_rpn.RPN_Conv.weight": torch.randn(512, 1024, 3, 3, generator=g) * math.sqrt(2.0 / (1024 * 9)),
+            "RCNN_rpn.RPN_Conv.bias": (torch.rand(512, generator=g) - 0.5) * 0.1,
+            "RCNN_rpn.RPN_cls_score.weight": torch.randn(24, 512, 1, 1, generator=g) * 0.004,
+            "RCNN_rpn.RPN_cls_score.bias": (torch.rand(24, generator=g) - 0.5) * 0.1,
+            "RCNN_rpn.RPN_bbox_pred.weight": torch.randn(48, 512, 1, 1, generator=g) * 0.01,
+            "RCNN_rpn.RPN_bbox_pred.bias": (torch.rand(48, generator=g) - 0.5) * 0.05}
+
+
+def rpn_base_anchors() -> np.ndarray:
+    """fasterrcnn_vg_rpn.py:110-118: 4 scales x 3 ratios around (0, 0), Python-double arithmetic, one rounding to fp32."""
+    rows = []
+    for scale in RPN_SCALES:
+        for ratio in RPN_RATIOS:
+            h = scale * RPN_STRIDE * (ratio ** 0.5)
+            w = scale * RPN_STRIDE / (ratio ** 0.5)
+            rows.append([-w / 2, -h / 2, w / 2, h / 2])
+    return np.array(rows, dtype=np.float32)
+
+
+def rpn_heads(rpn_sd, fmap: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """:78-92: 3x3 conv + ReLU, then the two 1x1 heads, re-laid as [H*W*12, 2] objectness logits and [H*W*12, 4] deltas."""
+    x = F.relu(F.conv2d(fmap, rpn_sd["RCNN_rpn.RPN_Conv.weight"], rpn_sd["RCNN_rpn.RPN_Conv.bias"], padding=1))
+    cls = F.conv2d(x, rpn_sd["RCNN_rpn.RPN_cls_score.weight"], rpn_sd["RCNN_rpn.RPN_cls_score.bias"])
+    box = F.conv2d(x, rpn_sd["RCNN_rpn.RPN_bbox_pred.weight"], rpn_sd["RCNN_rpn.RPN_bbox_pred.bias"])
+    return cls.permute(0, 2, 3, 1).reshape(-1, 2), box.permute(0, 2, 3, 1).reshape(-1, 4)
+
+
+def rpn_decode(cls: np.ndarray, box: np.ndarray, fh: int, fw: int, img_h: int, img_w: int) -> Tuple[np.ndarray, np.ndarray]:
+    """:85-104, 106-174: foreground probability (softmax over the pair), anchors (base + cell centre), deltas applied in fp32 with
+    one rounding per operation, clipped to the picture.  Returns (proposals [A,4], scores [A]), A = fh*fw*12, anchor fastest."""
+    f32 = np.float32
+    cls, box = cls.astype(f32), box.astype(f32)
+    m = np.maximum(cls[:, 0], cls[:, 1])
+    e0, e1 = np.exp(cls[:, 0] - m, dtype=f32), np.exp(cls[:, 1] - m, dtype=f32)
+    scores = (e1 / (e0 + e1)).astype(f32)
+    ys, xs = np.meshgrid(np.arange(fh) * RPN_STRIDE + RPN_STRIDE // 2, np.arange(fw) * RPN_STRIDE + RPN_STRIDE // 2, indexing="ij")
+    shifts = np.stack([xs, ys, xs, ys], axis=-1).reshape(-1, 1, 4).astype(f32)
+    anchors = (rpn_base_anchors()[None, :, :] + shifts).reshape(-1, 4).astype(f32)
+    widths, heights = anchors[:, 2] - anchors[:, 0], anchors[:, 3] - anchors[:, 1]
+    ctr_x, ctr_y = anchors[:, 0] + f32(0.5) * widths, anchors[:, 1] + f32(0.5) * heights
+    dw, dh = np.minimum(box[:, 2], f32(4.0)), np.minimum(box[:, 3], f32(4.0))
+    pcx, pcy = box[:, 0] * widths + ctr_x, box[:, 1] * heights + ctr_y
+    pw, ph = np.exp(dw, dtype=f32) * widths, np.exp(dh, dtype=f32) * heights
+    props = np.stack([pcx - f32(0.5) * pw, pcy - f32(0.5) * ph, pcx + f32(0.5) * pw, pcy + f32(0.5) * ph], axis=-1).astype(f32)
+    props[:, 0::2] = np.clip(props[:, 0::2], f32(0), f32(img_w))
+    props[:, 1::2] = np.clip(props[:, 1::2], f32(0), f32(img_h))
+    return props, scores
+
+
+def rpn_filter(props: np.ndarray, scores: np.ndarray, min_size: float = 16, pre_nms: int = 6000, post_nms: int = 300,
+               nms_thr: float = 0.7) -> np.ndarray:
+    """:442-469 (``_filter_proposals``): indices into ``props`` of the proposals that survive, in descending score order.  The
+    reference's ``topk`` among exactly tied scores is unspecified; this restatement keeps the stable order."""
+    w, h = props[:, 2] - props[:, 0], props[:, 3] - props[:, 1]
+    idx = np.nonzero((w >= np.float32(min_size)) & (h >= np.float32(min_size)))[0]
+    if len(idx) == 0:
+        return idx
+    order = idx[np.argsort(-scores[idx], kind="stable")][:pre_nms]
+    keep = nms(props[order], scores[order], nms_thr)[:post_nms]
+    return order[keep]
+
+
+def rpn_resize(w: int, h: int, target: int = 600, max_size: int = 1000) -> Tuple[int, int, float]:
+    """:373-385 (``_resize_image``): (new_w, new_h, scale)."""
+    scale = target / min(w, h)
+    if max(w, h) * scale > max_size:
+        scale = max_size / max(w, h)
+    return int(w * scale), int(h * scale), scale
+
+
+def rpn_pad_grid(num_needed: int, img_w: int, img_h: int) -> np.ndarray:
+    """:497-516: the grid cells appended when fewer than num_regions proposals survive."""
+    g = int(num_needed ** 0.5) + 1
+    cw, ch = img_w / g, img_h / g
+    rows = []
+    for i in range(g):
+        for j in range(g):
+            if len(rows) >= num_needed:
+                break
+            rows.append([j * cw, i * ch, min((j + 1) * cw, img_w), min((i + 1) * ch, img_h)])
+        if len(rows) >= num_needed:
+            break
+    return np.array(rows, dtype=np.float32).reshape(-1, 4)
+
+
+def vg_rpn_extract_features(sd, heads, rpn_sd, img: torch.Tensor, scale: float, orig_w: int, orig_h: int, num_regions: int = 36,
+                            region_scores: np.ndarray = None, kept: np.ndarray = None):
+    """fasterrcnn_vg_rpn.py:387-440 on a preprocessed picture [1,3,H,W]: (features [N,2048], spatial [N,5], boxes [N,4] in resized
+    pixels, kept proposal boxes, their region scores).  ``kept`` / ``region_scores`` override the RPN survivors / their class scores
+    (selection parity under given inputs)."""
+    h, w = img.shape[2], img.shape[3]
+    with torch.no_grad():
+        fmap = forward_base(sd, img)
+        if kept is None:
+            cls, box = rpn_heads(rpn_sd, fmap)
+            props, scores = rpn_decode(cls.numpy(), box.numpy(), fmap.shape[2], fmap.shape[3], h, w)
+            kept = props[rpn_filter(props, scores)]
+        if region_scores is None or len(kept) < num_regions:
+            s, top = vg_scores(sd, heads, fmap, kept) if len(kept) else (np.zeros(0, np.float32), np.zeros((0, 2048), np.float32))
+            region_scores = s if region_scores is None else region_scores
+        else:
+            top = None
+        boxes = kept
+        if len(kept) > num_regions:
+            idx = np.argsort(-region_scores.astype(np.float32), kind="stable")[:num_regions]
+            boxes = kept[idx]
+        elif len(kept) < num_regions:
+            boxes = np.concatenate([kept, rpn_pad_grid(num_regions - len(kept), w, h)], axis=0)[:num_regions]
+        rois = np.concatenate([np.zeros((len(boxes), 1), np.float32), boxes.astype(np.float32)], axis=1)
+        feats = forward_top(sd, torch.from_numpy(roi_pool(fmap.numpy(), rois, 14, 1.0 / 16.0))).numpy()
+    spatial = normalize_boxes((boxes.astype(np.float32) / np.float32(scale)).astype(np.float32), orig_w, orig_h)
+    return feats, spatial, boxes, kept, region_scores

@@ -342,7 +342,7 @@ def rowmax(x, out, col_begin=0, col_end=None):
 
 
 def select_regions(candidates, keep, num_keep, regions, img_w, img_h, *, boxes=None, spatial=None, index=None, feat_src=None,
-                   feat_dst=None, rois=None, batch_index=0):
+                   feat_dst=None, rois=None, batch_index=0, box_div=1.0):
     nk = int(num_keep.reshape(-1)[0])
     if nk <= 0:
         return
@@ -356,7 +356,7 @@ def select_regions(candidates, keep, num_keep, regions, img_w, img_h, *, boxes=N
         rois[:, 0] = float(batch_index)
         rois[:, 1:] = b
     if spatial is not None:
-        nb = b.clone()
+        nb = b / box_div
         nb[:, [0, 2]] /= img_w
         nb[:, [1, 3]] /= img_h
         nb = nb.clamp(0, 1)
@@ -365,8 +365,59 @@ def select_regions(candidates, keep, num_keep, regions, img_w, img_h, *, boxes=N
         feat_dst.copy_(feat_src[idx])
 
 
+def rpn_decode(heads, fh, fw, base_anchors, stride, img_h, img_w, min_size, boxes, scores, num_valid):
+    """fasterrcnn_vg_rpn.py:78-174 + the min-size test of :444-450 in torch."""
+    a = base_anchors.shape[0]
+    cls = heads[:, : 2 * a].reshape(-1, 2)
+    deltas = heads[:, 2 * a: 6 * a].reshape(-1, 4)
+    fg = F.softmax(cls, dim=-1)[:, 1]
+    sx = torch.arange(0, fw) * stride + stride // 2
+    sy = torch.arange(0, fh) * stride + stride // 2
+    sy, sx = torch.meshgrid(sy, sx, indexing="ij")
+    shifts = torch.stack([sx, sy, sx, sy], dim=-1).reshape(-1, 4)
+    anchors = (torch.from_numpy(base_anchors).unsqueeze(0) + shifts.unsqueeze(1)).reshape(-1, 4)
+    w, h = anchors[:, 2] - anchors[:, 0], anchors[:, 3] - anchors[:, 1]
+    cx, cy = anchors[:, 0] + 0.5 * w, anchors[:, 1] + 0.5 * h
+    pcx, pcy = deltas[:, 0] * w + cx, deltas[:, 1] * h + cy
+    pw, ph = torch.exp(deltas[:, 2].clamp(max=4.0)) * w, torch.exp(deltas[:, 3].clamp(max=4.0)) * h
+    p = torch.stack([pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph], dim=-1)
+    p[:, 0::2] = p[:, 0::2].clamp(0, img_w)
+    p[:, 1::2] = p[:, 1::2].clamp(0, img_h)
+    ok = ((p[:, 2] - p[:, 0]) >= min_size) & ((p[:, 3] - p[:, 1]) >= min_size)
+    boxes.copy_(p)
+    scores.copy_(torch.where(ok, fg, torch.full_like(fg, float("-inf"))))
+    num_valid.fill_(int(ok.sum()))
+
+
+def rank_sort_desc(scores, order, limit=None):
+    s = scores.clone()
+    if limit is not None:
+        s[int(limit.reshape(-1)[0]):] = float("-inf")
+    order[: s.numel()] = torch.sort(s, descending=True, stable=True)[1].to(torch.int32)
+    return order
+
+
+def gather_sorted(boxes, scores, order, num_valid, out_boxes, out_scores, count):
+    cap = out_boxes.shape[0]
+    n = min(cap, int(num_valid.reshape(-1)[0]))
+    idx = order[:n].long()
+    out_boxes.zero_()
+    out_scores.fill_(float("-inf"))
+    out_boxes[:n] = boxes[idx]
+    out_scores[:n] = scores[idx]
+    count.fill_(n)
+
+
+def nms_sorted(boxes, count, iou_threshold, keep, num_keep):
+    import torchvision
+    n = int(count.reshape(-1)[0])
+    k = torchvision.ops.nms(boxes[:n], torch.arange(n, 0, -1, dtype=torch.float32), iou_threshold)[: keep.numel()]
+    keep[: k.numel()] = k.to(torch.int32)
+    num_keep.fill_(k.numel())
+
+
 ROI_SIMULATED = ["stem_im2col", "im2col_nhwc", "maxpool_nhwc", "roi_pool_nhwc", "roi_align_nhwc", "avgpool_nhwc", "box_area_score",
-                 "nms", "nms_device", "rowmax", "select_regions"]
+                 "nms", "nms_device", "rowmax", "select_regions", "rpn_decode", "rank_sort_desc", "gather_sorted", "nms_sorted"]
 SIMULATED = ["gemm", "layernorm_fwd", "layernorm_bwd", "embed_text_fwd", "embed_text_bwd", "colsum", "cast_bf16", "cast_f32", "mask_bias",
              "i64_to_i32", "stage_batch", "dropout", "seed_advance", "act_bwd", "loc_embed_fwd", "loc_embed_bwd", "cls_ce_fwd", "cls_ce_bwd",
              "attention_fwd", "attention_bwd"]

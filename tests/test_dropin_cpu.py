@@ -37,6 +37,6 @@ def test_install_rebinds_the_reference_lookups():
     # the extractor factory now reaches our class (which refuses a CPU device instead of silently falling back)
     with pytest.raises(VbError):
         get_feature_extractor("resnet152_roi", device="cpu")
-    for name in ("resnet", "resnet_vg", "fasterrcnn_vg"):
+    for name in ("resnet", "resnet_vg", "fasterrcnn_vg", "fasterrcnn_vg_rpn"):
         with pytest.raises(VbError):
             get_feature_extractor(name, device="cpu")
