@@ -145,15 +145,18 @@ __global__ void maxpool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 // torchvision.ops.roi_pool semantics (csrc/ops/cpu/roi_pool_kernel.cpp): coordinates are rounded half away from zero
 // after scaling, a RoI is at least 1x1, bin borders are floor / ceil of multiples of roi_size / pooled_size, clipped to the
 // map; an empty bin gives 0; otherwise the maximum (first maximum in row-major scan order for argmax).
+// One thread per 16-byte piece (8 channels) of the output; ARGMAX is a compile-time switch (the extractors do not ask for it, and
+// tracking eight indices per thread doubled the instruction count of this instruction-bound kernel), indices are 32-bit.
+template <bool ARGMAX>
 __global__ void roi_pool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ rois,
                                      __nv_bfloat16* __restrict__ y, int* __restrict__ argmax, int num_rois, int n, int h,
                                      int w, int c, int ph, int pw, float spatial_scale) {
   const int cv = c >> 3;
-  const long long total = (long long)num_rois * ph * pw * cv;
-  const long long step = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
+  const unsigned total = (unsigned)num_rois * ph * pw * cv;
+  const unsigned step = gridDim.x * blockDim.x;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
     const int ci = (int)(idx % cv);
-    long long r = idx / cv;
+    unsigned r = idx / cv;
     const int px = (int)(r % pw); r /= pw;
     const int py = (int)(r % ph); r /= ph;
     const int roi = (int)r;
@@ -177,24 +180,31 @@ __global__ void roi_pool_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const 
     wend = min(max(wend + roi_start_w, 0), w);
     const bool empty = (hend <= hstart) || (wend <= wstart) || b < 0 || b >= n;
     float m[8];
-    int am[8];
+    int am[ARGMAX ? 8 : 1];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { m[i] = empty ? 0.f : -FLT_MAX; am[i] = -1; }
+    for (int i = 0; i < 8; ++i) m[i] = empty ? 0.f : -FLT_MAX;
+    if (ARGMAX) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) am[ARGMAX ? i : 0] = -1;
+    }
     if (!empty) {
+      const __nv_bfloat16* base = x + ((long long)b * h * w) * c + ci * 8;
       for (int iy = hstart; iy < hend; ++iy)
         for (int ix = wstart; ix < wend; ++ix) {
           float v[8];
-          ld8b(x + (((long long)b * h + iy) * w + ix) * c + ci * 8, v);
+          ld8b(base + (long long)(iy * w + ix) * c, v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (v[i] > m[i]) { m[i] = v[i]; am[i] = iy * w + ix; }
+          for (int i = 0; i < 8; ++i) {
+            if (ARGMAX) { if (v[i] > m[i]) { m[i] = v[i]; am[ARGMAX ? i : 0] = iy * w + ix; } }
+            else m[i] = fmaxf(m[i], v[i]);
+          }
         }
     }
     const long long o = (((long long)roi * ph + py) * pw + px) * c + ci * 8;
     *reinterpret_cast<uint4*>(y + o) = pack8(m);
-    if (argmax != nullptr) {
+    if (ARGMAX) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) argmax[o + i] = am[i];
+      for (int i = 0; i < 8; ++i) argmax[o + i] = am[ARGMAX ? i : 0];
     }
   }
 }
@@ -352,8 +362,13 @@ extern "C" int vb_roi_pool_nhwc(const void* x, const float* rois, void* y, int32
   VB_REQUIRE(al16(x) && al16(y) && ph > 0 && pw > 0, "alignment / pooled size");
   if (num_rois == 0) return VB_OK;
   const long long total = (long long)num_rois * ph * pw * (c / 8);
-  roi_pool_nhwc_kernel<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rois, (__nv_bfloat16*)y,
-                                                                                argmax, num_rois, n, h, w, c, ph, pw, spatial_scale);
+  VB_REQUIRE(total < (1ll << 31), "too many RoI bins for the 32-bit index");
+  if (argmax != nullptr)
+    roi_pool_nhwc_kernel<true><<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rois, (__nv_bfloat16*)y,
+                                                                                        argmax, num_rois, n, h, w, c, ph, pw, spatial_scale);
+  else
+    roi_pool_nhwc_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rois, (__nv_bfloat16*)y,
+                                                                                         nullptr, num_rois, n, h, w, c, ph, pw, spatial_scale);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;
 }

@@ -583,14 +583,18 @@ __global__ void loc_embed_bwd_kernel(const __nv_bfloat16* ds, const float* loc, 
 // ------------------------------------------------------------------------------------------------ classifier tail + CE
 // logits = h W^T + b  (Linear(1024, num_labels), vilbert_facebook_arch.py:577), CrossEntropyLoss mean (:637-639).
 // One block; fp32 master weights are read directly (C <= 8 rows).
-__global__ void __launch_bounds__(256) cls_fwd_kernel(const __nv_bfloat16* h, const float* w, const float* bias,
+__global__ void __launch_bounds__(1024) cls_fwd_kernel(const __nv_bfloat16* h, const float* w, const float* bias,
                                                       const int* labels, float* logits, float* probs, float* loss,
                                                       int bsz, int kdim, int c) {
   __shared__ float s_logits[8192];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int o = warp; o < bsz * c; o += 8) {
+  // one warp per (sample, class) dot product, 32 of them in flight (the 8-warp version walked the 32 outputs of the bs-16 /
+  // 2-class head in four dependent rounds: 15 us at the END of the forward's critical path)
+  const int nwarps = blockDim.x >> 5;
+  for (int o = warp; o < bsz * c; o += nwarps) {
     const int bi = o / c, ci = o % c;
     float acc = 0.f;
+#pragma unroll 4
     for (int k = lane; k < kdim; k += 32) acc += __bfloat162float(h[(long long)bi * kdim + k]) * w[(long long)ci * kdim + k];
     acc = warp_sum(acc);
     if (lane == 0) { s_logits[o] = acc + bias[ci]; logits[o] = acc + bias[ci]; }
@@ -638,19 +642,23 @@ __global__ void __launch_bounds__(256) cls_bwd_kernel(const __nv_bfloat16* h, co
     s_dl[o] = g;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < kdim; k += blockDim.x) {
+  // the hidden dimension is spread over the GRID (every block recomputes the tiny dlogits above): one block of 256 threads
+  // walked 4 x (c + 1) x bsz dependent loads = 30 us at the START of the backward's critical path
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < kdim; k += gridDim.x * blockDim.x) {
     for (int ci = 0; ci < c; ++ci) {
       float acc = 0.f;
+#pragma unroll 8
       for (int bi = 0; bi < bsz; ++bi) acc += s_dl[bi * c + ci] * __bfloat162float(h[(long long)bi * kdim + k]);
       if (dw) dw[(long long)ci * kdim + k] = acc;
     }
+#pragma unroll 4
     for (int bi = 0; bi < bsz; ++bi) {
       float acc = 0.f;
       for (int ci = 0; ci < c; ++ci) acc += s_dl[bi * c + ci] * w[(long long)ci * kdim + k];
       dh[(long long)bi * kdim + k] = __float2bfloat16_rn(acc);
     }
   }
-  if (db && threadIdx.x < c) {
+  if (db && blockIdx.x == 0 && threadIdx.x < c) {
     float acc = 0.f;
     for (int bi = 0; bi < bsz; ++bi) acc += s_dl[bi * c + threadIdx.x];
     db[threadIdx.x] = acc;
@@ -940,7 +948,7 @@ extern "C" int vb_loc_embed_bwd(const void* ds, const float* loc, float* dw, flo
 extern "C" int vb_cls_ce_fwd(const void* h, const float* w, const float* bias, const int32_t* labels, float* logits,
                              float* probs, float* loss, int32_t bsz, int32_t kdim, int32_t c, void* stream) {
   VB_REQUIRE(h && w && bias && logits && probs && bsz > 0 && bsz * c <= 8192 && c <= 8 && kdim > 0, "bad classifier arguments (B*C <= 8192, C <= 8)");
-  cls_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)h, w, bias, labels, logits, probs, loss, bsz, kdim, c);
+  cls_fwd_kernel<<<1, (bsz * c >= 32) ? 1024 : 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)h, w, bias, labels, logits, probs, loss, bsz, kdim, c);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;
 }
@@ -949,7 +957,7 @@ extern "C" int vb_cls_ce_bwd(const void* h, const float* w, const int32_t* label
                              const float* dloss, const float* dlogits_ext, float* dw, float* db, void* dh, int32_t bsz,
                              int32_t kdim, int32_t c, void* stream) {
   VB_REQUIRE(h && w && probs && dh && bsz > 0 && bsz * c <= 8192 && c <= 8 && kdim > 0, "bad classifier arguments (B*C <= 8192, C <= 8)");
-  cls_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)h, w, labels, probs, dloss, dlogits_ext, dw, db,
+  cls_bwd_kernel<<<(kdim + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)h, w, labels, probs, dloss, dlogits_ext, dw, db,
                                                       (__nv_bfloat16*)dh, bsz, kdim, c);
   VB_CUDA_CHECK(cudaGetLastError());
   return VB_OK;

@@ -866,8 +866,20 @@ class _Engine:
         s_v = pl.s_v if self.two_streams else s_t
         sides_t = [pl.s_tw] if self.side_streams else []
         sides_v = [pl.s_vw] if self.side_streams else []
-        # gradients that are accumulated with atomics start from zero (biases, LayerNorm, location weights, tables)
-        f.grad[f.w_end:f.s_end].zero_()
+        # gradients that are accumulated with atomics start from zero (biases, LayerNorm, location weights, tables).  The word
+        # embedding table is 94 of the 100 MB and is only touched by the LAST kernel of the pass: its fill runs on a side stream
+        # (16 us off the head of the critical path), the small rest here
+        o_word = f.offsets.get("bert.embeddings.word_embeddings.weight", f.s_end)
+        word_zeroed = None
+        if self.side_streams and f.w_end < o_word < f.s_end:
+            f.grad[f.w_end:o_word].zero_()
+            pl.s_tw.wait_stream(s_t)
+            with torch.cuda.stream(pl.s_tw):
+                f.grad[o_word:f.s_end].zero_()
+                word_zeroed = torch.cuda.Event()
+                word_zeroed.record(pl.s_tw)
+        else:
+            f.grad[f.w_end:f.s_end].zero_()
         if self.wgrad_split:
             # weight gradients are produced by split-K GEMMs that reduce-add into the buffer: zero it once, on the side
             # stream(s) that own it, while the head of the backward chain runs
@@ -943,6 +955,8 @@ class _Engine:
             ops.loc_embed_bwd(g_s, pl.loc, f.g(ve + ".image_location_embeddings.weight"),
                               f.g(ve + ".image_location_embeddings.bias"))
         e = "bert.embeddings"
+        if word_zeroed is not None:
+            s_t.wait_event(word_zeroed)
         ops.embed_text_bwd(dy_t[it_], pl.ids, pl.types, f.m(e + ".word_embeddings.weight").view(-1, H),
                            f.m(e + ".position_embeddings.weight").view(-1, H),
                            f.m(e + ".token_type_embeddings.weight").view(-1, H), f.m(e + ".LayerNorm.weight"),
