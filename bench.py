@@ -250,6 +250,33 @@ def time_roi_stage(torch, peaks):
             out["legs"].append({"image": size, "pool": f"{mode}-{roi}", "batch": b, "ms": ms, "images_per_s": b / ms * 1e3,
                                 "tflops": gf * b / ms, "frac_of_burst_bf16": gf * b / ms / peaks["bf16_burst"]})
         del ext
+    # the Visual Genome Faster R-CNN region extractors (row f-4) on the same kernels, random-init weights, their scored branches
+    # switched on as a checkpoint would: ms per picture of the whole CUDA graph (trunk + proposals + scoring + selection)
+    try:
+        from multimodal_classification_b200.fasterrcnn_vg import FasterRCNNVGExtractor
+        from multimodal_classification_b200.fasterrcnn_vg_rpn import FasterRCNNVGRPNExtractor
+        torch.manual_seed(0)
+        vg = FasterRCNNVGExtractor(weights_path="/nonexistent/vg.pth", device="cuda", weights=None)
+        vg.has_vg_weights = True
+        x = torch.randn(1, 3, 600, 1000, device="cuda")
+        rpn = FasterRCNNVGRPNExtractor(weights_path="/nonexistent/vg.pth", device="cuda", weights=None)
+        y = torch.randn(1, 3, 600, 800, device="cuda")
+        for name, fn in (("fasterrcnn_vg 600x1000, 200 scored candidates -> 36 regions", lambda: vg.extract_batch(x)),
+                         ("fasterrcnn_vg_rpn 600x800, 22800 anchors -> NMS -> 300 scored -> 36 regions",
+                          lambda: rpn.extract_preprocessed(y, 6.25, 128, 96))):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                fn()
+            e.record()
+            torch.cuda.synchronize()
+            out.setdefault("vg_extractors", []).append({"extractor": name, "ms_per_picture": s.elapsed_time(e) / 10})
+        del vg, rpn
+    except Exception as err:      # the headline line must still print
+        out["vg_extractors"] = {"error": repr(err)[:200]}
     # the pooling kernels alone: 36 boxes on one C4 map (stride 16, 1024 channels), bytes = map read once + output written once
     for size, roi, mode in ((600, 14, "roi_pool"), (448, 7, "roi_align")):
         hw = (size + 15) // 16

@@ -1207,8 +1207,13 @@ class ViLBERTForClassification(nn.Module):
         ver = eng.flat.versions()
         if ver != eng.flat._version:
             upd = eng.flat._updated
-            if eng.refresh_in_graph:
-                eng.refresh_pending = True        # the forward about to run casts the shadows block by block beside its first layers
+            # Two regimes.  The GPU is still busy with the previous step (the host runs ahead): the forward about to run carries
+            # the refresh as a branch of its graph, block by block beside its first layers.  The GPU has already drained up to
+            # the optimizer's update (the reference's loop reads loss.item() every step, so the host is the late one): cast now,
+            # on the side stream, beside the batch copy and the rest of this call's host work -- the window is free anyway.
+            idle = upd is not None and upd[1] == ver and eng.refresh_stream is not None and upd[0].query()
+            if eng.refresh_in_graph and not idle:
+                eng.refresh_pending = True
             elif upd is not None and upd[1] == ver and eng.refresh_stream is not None:
                 # nothing touched the parameters after the optimizer's hook: refresh beside whatever was queued since
                 # (the next batch's host-to-device copy), the forward waits for it below
