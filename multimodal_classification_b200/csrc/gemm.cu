@@ -231,7 +231,8 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
 // instructions with 32-wide instruction-level parallelism and no flag tests (two epilogue warps per scheduler cannot hide
 // branch / LDS latencies, and the code runs once per launch from a cold instruction cache); everything else takes the generic
 // kernel with run-time flags.
-enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_GELU_PRE = 2, EPI_AUX_ADD = 3, EPI_AUX_GELUGRAD = 4, EPI_F32 = 5 };
+// EPI_BN_RELU / EPI_BN_ADD_RELU: the ResNet convolutions (folded-BatchNorm scale + bias, [+ bottleneck identity,] ReLU, bf16 out)
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_GELU_PRE = 2, EPI_AUX_ADD = 3, EPI_AUX_GELUGRAD = 4, EPI_F32 = 5, EPI_BN_RELU = 6, EPI_BN_ADD_RELU = 7 };
 
 // x / d for x * d < 2^32, d >= 1, with magic = ceil(2^32 / d) computed on the host (d = 1 -> magic 0 = "identity")
 __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return magic == 0u ? x : __umulhi(x, magic); }
@@ -254,25 +255,29 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+  if constexpr (EPI == EPI_BN_RELU || EPI == EPI_BN_ADD_RELU) {
+    const float4 s0 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u), s1 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u + 16u);
+    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+  }
   if constexpr (EPI == EPI_GENERIC) {
     if (s_scale != 0u) {
       const float4 s0 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u), s1 = lds_f4(s_scale + static_cast<uint32_t>(g) * 32u + 16u);
       v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
     }
   }
-  if constexpr (EPI == EPI_GENERIC || EPI == EPI_BIAS || EPI == EPI_GELU_PRE) {
+  if constexpr (EPI == EPI_GENERIC || EPI == EPI_BIAS || EPI == EPI_GELU_PRE || EPI == EPI_BN_RELU || EPI == EPI_BN_ADD_RELU) {
     const float4 b0 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u), b1 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u + 16u);
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
   if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact))
     sts_u4(xrow + ((static_cast<uint32_t>(g) ^ swz64) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  if (EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || (EPI == EPI_GENERIC && p.aux_mode != VB_AUX_NONE)) {
+  if (EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_BN_ADD_RELU || (EPI == EPI_GENERIC && p.aux_mode != VB_AUX_NONE)) {
     // my row of the warp's aux box (TMA-loaded, 64-byte rows, 64B swizzle): piece g
     const uint4 aux = lds_u4(arow + ((static_cast<uint32_t>(g) ^ swz64) << 4));
     const float2 a0 = unpack_bf16x2(aux.x), a1 = unpack_bf16x2(aux.y), a2 = unpack_bf16x2(aux.z), a3 = unpack_bf16x2(aux.w);
     const float av[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-    if (EPI == EPI_AUX_ADD || (EPI == EPI_GENERIC && p.aux_mode == VB_AUX_ADD)) {
+    if (EPI == EPI_AUX_ADD || EPI == EPI_BN_ADD_RELU || (EPI == EPI_GENERIC && p.aux_mode == VB_AUX_ADD)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] += av[i];
     } else {
@@ -288,7 +293,7 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
   if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.act == VB_ACT_GELU)) {
 #pragma unroll
     for (int i = 0; i < 8; i += 2) gelu_fast2(v[i], v[i + 1]);
-  } else if (EPI == EPI_GENERIC && p.act == VB_ACT_RELU) {
+  } else if (EPI == EPI_BN_RELU || EPI == EPI_BN_ADD_RELU || (EPI == EPI_GENERIC && p.act == VB_ACT_RELU)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.0f);
   } else if (EPI == EPI_GENERIC && p.act == VB_ACT_TANH) {
@@ -634,7 +639,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       // its TMEM load (second register buffer) and its aux box (TMA into the warp's other aux box).  Staging boxes alternate, so
       // a chunk is staged while the previous store is still reading its box.  Iteration -1 of the CTA's first tile is a dry run on
       // zeros while the main loop is still computing: it pulls the epilogue code into the instruction cache (nothing is stored).
-      constexpr bool HAS_AUX = EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_GENERIC;
+      constexpr bool HAS_AUX = EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_BN_ADD_RELU || EPI == EPI_GENERIC;
       const bool use_aux = HAS_AUX && has_aux;
       const int my_chunks = (nch - half + 1) / 2;
       uint32_t r[32], rn[32];
@@ -1030,7 +1035,13 @@ static TileChoice pick_config(const vb_gemm_args& a) {
 // Which compiled epilogue serves this call (anything unusual -> the generic kernel with run-time flags)
 static int pick_epilogue(const vb_gemm_args& a) {
   static const bool generic_only = env_int("VB_GEMM_GENERIC_EPI", 0) != 0;
-  if (generic_only || a.scale != nullptr) return EPI_GENERIC;
+  if (generic_only) return EPI_GENERIC;
+  if (a.scale != nullptr) {
+    const bool bn = a.bias != nullptr && !a.d_is_f32 && a.d_preact == nullptr && a.act == VB_ACT_RELU;
+    if (bn && a.aux_mode == VB_AUX_NONE) return EPI_BN_RELU;
+    if (bn && a.aux_mode == VB_AUX_ADD) return EPI_BN_ADD_RELU;
+    return EPI_GENERIC;
+  }
   if (a.d_is_f32) return (a.bias == nullptr && a.act == VB_ACT_NONE && a.aux_mode == VB_AUX_NONE) ? EPI_F32 : EPI_GENERIC;
   if (a.d_preact != nullptr) return (a.act == VB_ACT_GELU && a.aux_mode == VB_AUX_NONE) ? EPI_GELU_PRE : EPI_GENERIC;
   if (a.aux_mode != VB_AUX_NONE)
@@ -1043,13 +1054,21 @@ static int pick_epilogue(const vb_gemm_args& a) {
 template <int CG, int NP, int OCC>
 static int dispatch_major(const vb_gemm_args& a, int bn, int splits, cudaStream_t s) {
   const int epi = CG == 2 ? pick_epilogue(a) : EPI_GENERIC;
-  if (a.conv_kh > 0) {       // implicit-GEMM convolution: generic epilogue (folded BatchNorm scale / bias, residual, ReLU), one CTA per SM
-    if constexpr (OCC == 1) return launch_gemm<false, false, CG, NP, 1, EPI_GENERIC, true>(a, bn, splits, s);
-    else { vb_set_last_error("vb_gemm_bf16", "convolution kernels are built for one CTA per SM"); return VB_ERR_UNSUPPORTED; }
+  if (a.conv_kh > 0) {       // implicit-GEMM convolution (one CTA per SM): BatchNorm + ReLU epilogue compiled in, anything else generic
+    if constexpr (OCC == 1) {
+      if constexpr (CG == 2) {
+        if (epi == EPI_BN_RELU) return launch_gemm<false, false, CG, NP, 1, EPI_BN_RELU, true>(a, bn, splits, s);
+      }
+      return launch_gemm<false, false, CG, NP, 1, EPI_GENERIC, true>(a, bn, splits, s);
+    } else { vb_set_last_error("vb_gemm_bf16", "convolution kernels are built for one CTA per SM"); return VB_ERR_UNSUPPORTED; }
   }
   if constexpr (CG == 2) {
     if (!a.a_mn_major && !a.b_mn_major) {
       if (epi == EPI_BIAS) return launch_gemm<false, false, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);
+      if constexpr (OCC == 1) {      // the 1x1 convolutions of the ResNet trunk (the activation itself is the operand)
+        if (epi == EPI_BN_RELU) return launch_gemm<false, false, CG, NP, OCC, EPI_BN_RELU>(a, bn, splits, s);
+        if (epi == EPI_BN_ADD_RELU) return launch_gemm<false, false, CG, NP, OCC, EPI_BN_ADD_RELU>(a, bn, splits, s);
+      }
       if (epi == EPI_GELU_PRE) return launch_gemm<false, false, CG, NP, OCC, EPI_GELU_PRE>(a, bn, splits, s);
     } else if (!a.a_mn_major && a.b_mn_major) {
       if (epi == EPI_BIAS) return launch_gemm<false, true, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);

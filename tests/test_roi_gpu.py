@@ -131,11 +131,21 @@ def test_implicit_gemm_convolution_equals_explicit_im2col(case):
     res = torch.randn(n * ho * wo, cout, generator=g).to(torch.bfloat16).cuda()
     col = torch.empty(n * ho * wo, k * k * cin, dtype=torch.bfloat16, device="cuda")
     ops.im2col_nhwc(x, col, k, k, stride, pad)
-    kw = dict(scale=scale, bias=bias, act=ops.ACT_RELU, aux=res, aux_mode=ops.AUX_ADD)
+    # BatchNorm + ReLU (what the trunk's 3x3s run): both calls take the same compiled epilogue -> bit-identical
+    kw = dict(scale=scale, bias=bias, act=ops.ACT_RELU)
     explicit = ops.gemm(col, wt, torch.empty(n * ho * wo, cout, dtype=torch.bfloat16, device="cuda"), **kw)
     implicit = ops.gemm(x, wt, torch.full((n * ho * wo, cout), float("nan"), dtype=torch.bfloat16, device="cuda"), conv=(k, k, stride, pad), **kw)
     torch.cuda.synchronize()
     assert torch.equal(implicit, explicit), float((implicit.float() - explicit.float()).abs().max())
+    # ... + residual: the convolution takes the generic epilogue, the plain GEMM the compiled BatchNorm + residual + ReLU one; they
+    # contract scale / bias / residual into FMAs differently, i.e. agree to an fp32 rounding = at most one bf16 ulp after the store
+    kw = dict(scale=scale, bias=bias, act=ops.ACT_RELU, aux=res, aux_mode=ops.AUX_ADD)
+    explicit = ops.gemm(col, wt, torch.empty(n * ho * wo, cout, dtype=torch.bfloat16, device="cuda"), **kw)
+    implicit = ops.gemm(x, wt, torch.full((n * ho * wo, cout), float("nan"), dtype=torch.bfloat16, device="cuda"), conv=(k, k, stride, pad), **kw)
+    torch.cuda.synchronize()
+    d = (implicit.float() - explicit.float()).abs()
+    assert bool((d <= explicit.float().abs() * 2.0 ** -7 + 1e-4).all()), float(d.max())      # (+ a floor for sums that cancel to ~0 before the ReLU)
+    assert float((d > 0).float().mean()) <= 1e-2
     w4 = wt.float().view(cout, k, k, cin).permute(0, 3, 1, 2)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4, stride=stride, padding=pad) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1)
     ref = F.relu(ref.permute(0, 2, 3, 1).reshape(n * ho * wo, cout) + res.float())
