@@ -51,7 +51,8 @@ typedef enum vb_act { VB_ACT_NONE = 0, VB_ACT_GELU = 1, VB_ACT_RELU = 2, VB_ACT_
 typedef enum vb_aux_mode {
   VB_AUX_NONE = 0,
   VB_AUX_ADD = 1,          /* v += aux[m,n]            (residual, before the activation) */
-  VB_AUX_MUL_GELU_GRAD = 2 /* v *= gelu'(aux[m,n])     (dgrad fused with the erf-GELU backward) */
+  VB_AUX_MUL_GELU_GRAD = 2,/* v *= gelu'(aux[m,n])     (dgrad fused with the erf-GELU backward) */
+  VB_AUX_MUL = 3           /* v *= aux[m,n]            (the same dgrad when the forward stored gelu' itself: preact_grad) */
 } vb_aux_mode;
 
 typedef struct vb_gemm_args {
@@ -79,6 +80,10 @@ typedef struct vb_gemm_args {
    * column (ky*kw + kx)*c + ci, d the NHWC output [conv_n*ho*wo, n]; m = conv_n*ho*wo, k = conv_kh*conv_kw*conv_c, lda unused.
    * The A tiles are fetched by TMA in im2col mode (zero padding by out-of-bounds fill): no [pixels, kh*kw*c] buffer exists. */
   int32_t conv_n, conv_h, conv_w, conv_c, conv_kh, conv_kw, conv_stride, conv_pad;
+  /* With act = VB_ACT_GELU and d_preact: store GELU'(pre-activation) in d_preact instead of the pre-activation.  The forward
+   * epilogue has the tanh of the GELU anyway, so the derivative costs a few FMAs there and the backward GEMM (VB_AUX_MUL) only
+   * multiplies (vilbert_facebook_arch.py:184-185 and autograd thereof). */
+  int32_t preact_grad;
 } vb_gemm_args;
 
 int vb_gemm_bf16(const vb_gemm_args* args, void* stream);

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VB_LIB") or os.path.join(_HERE, "libvilbert_b200.so")
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
-AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD = 0, 1, 2
+AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_MUL = 0, 1, 2, 3
 
 
 class VbError(RuntimeError):
@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("b_streamed", C.c_int32), ("d_streamed", C.c_int32),
         ("conv_n", C.c_int32), ("conv_h", C.c_int32), ("conv_w", C.c_int32), ("conv_c", C.c_int32),
         ("conv_kh", C.c_int32), ("conv_kw", C.c_int32), ("conv_stride", C.c_int32), ("conv_pad", C.c_int32),
+        ("preact_grad", C.c_int32),
     ]
 
 

@@ -397,6 +397,18 @@ __device__ __forceinline__ void gelu_fast_grad2(float x0, float x1, float& g0, f
   g0 = fmaf(0.5f * x0 * fmaf(-t.x, t.x, 1.0f), d0, fmaf(0.5f, t.x, 0.5f));
   g1 = fmaf(0.5f * x1 * fmaf(-t.y, t.y, 1.0f), d1, fmaf(0.5f, t.y, 0.5f));
 }
+// x Phi(x) AND its derivative for a pair, from one tanh per pair: x0 / x1 become the activation, g0 / g1 the derivative
+__device__ __forceinline__ void gelu_fast2_with_grad(float& x0, float& x1, float& g0, float& g1) {
+  const float2 t = tanh2_fast(phi_tanh_arg(x0), phi_tanh_arg(x1));
+  const float u0 = x0 * x0, u1 = x1 * x1;
+  const float d0 = u0 < 36.0f ? fmaf(u0, fmaf(u0, 5.0f * -3.51902393e-4f, 3.0f * 3.70080200e-2f), 7.97505275e-1f) : 0.0f;
+  const float d1 = u1 < 36.0f ? fmaf(u1, fmaf(u1, 5.0f * -3.51902393e-4f, 3.0f * 3.70080200e-2f), 7.97505275e-1f) : 0.0f;
+  const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+  g0 = fmaf(h0 * fmaf(-t.x, t.x, 1.0f), d0, fmaf(0.5f, t.x, 0.5f));
+  g1 = fmaf(h1 * fmaf(-t.y, t.y, 1.0f), d1, fmaf(0.5f, t.y, 0.5f));
+  x0 = fmaf(h0, t.x, h0);
+  x1 = fmaf(h1, t.y, h1);
+}
 __device__ __forceinline__ float gelu_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_fast(phi_tanh_arg(x)), hx);

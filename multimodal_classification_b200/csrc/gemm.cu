@@ -89,7 +89,7 @@ struct GemmKernelParams {
   long long ld_aux;
   int m, n, k;
   int bn;           // tile width (columns of the output per CTA pair / per lone CTA)
-  int d_is_f32, reduce_add, act, aux_mode, has_preact;
+  int d_is_f32, reduce_add, act, aux_mode, has_preact, preact_grad;
   int splits, kb_per_split;
   int m_tiles, n_tiles;
   int stages;       // depth of the operand ring
@@ -232,7 +232,9 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
 // branch / LDS latencies, and the code runs once per launch from a cold instruction cache); everything else takes the generic
 // kernel with run-time flags.
 // EPI_BN_RELU / EPI_BN_ADD_RELU: the ResNet convolutions (folded-BatchNorm scale + bias, [+ bottleneck identity,] ReLU, bf16 out)
-enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_GELU_PRE = 2, EPI_AUX_ADD = 3, EPI_AUX_GELUGRAD = 4, EPI_F32 = 5, EPI_BN_RELU = 6, EPI_BN_ADD_RELU = 7 };
+enum { EPI_GENERIC = 0, EPI_BIAS = 1, EPI_GELU_PRE = 2, EPI_AUX_ADD = 3, EPI_AUX_GELUGRAD = 4, EPI_F32 = 5, EPI_BN_RELU = 6, EPI_BN_ADD_RELU = 7,
+       EPI_GELU_GRADPRE = 8,   // bias + GELU, second output = GELU'(pre-activation) (what the backward multiplies by)
+       EPI_AUX_MUL = 9 };      // acc * aux (the dgrad of a GELU layer whose forward stored GELU')
 
 // x / d for x * d < 2^32, d >= 1, with magic = ceil(2^32 / d) computed on the host (d = 1 -> magic 0 = "identity")
 __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return magic == 0u ? x : __umulhi(x, magic); }
@@ -265,14 +267,24 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
       v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
     }
   }
-  if constexpr (EPI == EPI_GENERIC || EPI == EPI_BIAS || EPI == EPI_GELU_PRE || EPI == EPI_BN_RELU || EPI == EPI_BN_ADD_RELU) {
+  if constexpr (EPI == EPI_GENERIC || EPI == EPI_BIAS || EPI == EPI_GELU_PRE || EPI == EPI_GELU_GRADPRE || EPI == EPI_BN_RELU ||
+                EPI == EPI_BN_ADD_RELU) {
     const float4 b0 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u), b1 = lds_f4(s_bias + static_cast<uint32_t>(g) * 32u + 16u);
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
-  if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact))
+  if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact && !p.preact_grad))
     sts_u4(xrow + ((static_cast<uint32_t>(g) ^ swz64) << 4), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  if (EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_BN_ADD_RELU || (EPI == EPI_GENERIC && p.aux_mode != VB_AUX_NONE)) {
+  if (EPI == EPI_GELU_GRADPRE || (EPI == EPI_GENERIC && p.has_preact && p.preact_grad)) {
+    // GELU and its derivative from ONE tanh per pair: the forward has the tanh anyway, the backward then only multiplies
+    float gr[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) gelu_fast2_with_grad(v[i], v[i + 1], gr[i], gr[i + 1]);
+    sts_u4(xrow + ((static_cast<uint32_t>(g) ^ swz64) << 4), pack_bf16x2(gr[0], gr[1]), pack_bf16x2(gr[2], gr[3]),
+           pack_bf16x2(gr[4], gr[5]), pack_bf16x2(gr[6], gr[7]));
+  }
+  if (EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_AUX_MUL || EPI == EPI_BN_ADD_RELU ||
+      (EPI == EPI_GENERIC && p.aux_mode != VB_AUX_NONE)) {
     // my row of the warp's aux box (TMA-loaded, 64-byte rows, 64B swizzle): piece g
     const uint4 aux = lds_u4(arow + ((static_cast<uint32_t>(g) ^ swz64) << 4));
     const float2 a0 = unpack_bf16x2(aux.x), a1 = unpack_bf16x2(aux.y), a2 = unpack_bf16x2(aux.z), a3 = unpack_bf16x2(aux.w);
@@ -280,6 +292,9 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
     if (EPI == EPI_AUX_ADD || EPI == EPI_BN_ADD_RELU || (EPI == EPI_GENERIC && p.aux_mode == VB_AUX_ADD)) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] += av[i];
+    } else if (EPI == EPI_AUX_MUL || (EPI == EPI_GENERIC && p.aux_mode == VB_AUX_MUL)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= av[i];
     } else {
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
@@ -290,7 +305,9 @@ __device__ __forceinline__ void epilogue_octet(const GemmKernelParams& p, const 
       }
     }
   }
-  if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.act == VB_ACT_GELU)) {
+  if (EPI == EPI_GELU_GRADPRE || (EPI == EPI_GENERIC && p.has_preact && p.preact_grad && p.act == VB_ACT_GELU)) {
+    // (the activation itself was produced together with its derivative above)
+  } else if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.act == VB_ACT_GELU)) {
 #pragma unroll
     for (int i = 0; i < 8; i += 2) gelu_fast2(v[i], v[i + 1]);
   } else if (EPI == EPI_BN_RELU || EPI == EPI_BN_ADD_RELU || (EPI == EPI_GENERIC && p.act == VB_ACT_RELU)) {
@@ -639,7 +656,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       // its TMEM load (second register buffer) and its aux box (TMA into the warp's other aux box).  Staging boxes alternate, so
       // a chunk is staged while the previous store is still reading its box.  Iteration -1 of the CTA's first tile is a dry run on
       // zeros while the main loop is still computing: it pulls the epilogue code into the instruction cache (nothing is stored).
-      constexpr bool HAS_AUX = EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_BN_ADD_RELU || EPI == EPI_GENERIC;
+      constexpr bool HAS_AUX = EPI == EPI_AUX_ADD || EPI == EPI_AUX_GELUGRAD || EPI == EPI_AUX_MUL || EPI == EPI_BN_ADD_RELU || EPI == EPI_GENERIC;
       const bool use_aux = HAS_AUX && has_aux;
       const int my_chunks = (nch - half + 1) / 2;
       uint32_t r[32], rn[32];
@@ -712,7 +729,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
               else              tma_store_2d_hint(&tma_d, smem + L.out + (ewarp * p.nbuf + sbuf) * GEMM_BOX_F32, c0, r0, p.d_policy ? p.d_policy : L2_EVICT_NORMAL);
             } else {
               tma_store_2d(&tma_d, smem + L.out + (ewarp * p.nbuf + sbuf) * GEMM_BOX_BF16, c0, r0);
-              if (EPI == EPI_GELU_PRE || (EPI == EPI_GENERIC && p.has_preact))
+              if (EPI == EPI_GELU_PRE || EPI == EPI_GELU_GRADPRE || (EPI == EPI_GENERIC && p.has_preact))
                 tma_store_2d(&tma_x, smem + L.x + (ewarp * p.nbuf + sbuf) * GEMM_BOX_BF16, c0, r0);
             }
           }
@@ -904,6 +921,7 @@ static int launch_gemm(const vb_gemm_args& a, int bn, int splits, cudaStream_t s
   p.bn = bn;
   p.d_is_f32 = a.d_is_f32; p.act = a.act; p.aux_mode = a.aux_mode;
   p.has_preact = a.d_preact != nullptr;
+  p.preact_grad = a.preact_grad;
   p.m_tiles = (a.m + GEMM_BM * CG - 1) / (GEMM_BM * CG);
   p.n_tiles = ((a.n + bn - 1) / bn + NP - 1) / NP;   // N steps of a whole cluster (NP tiles side by side)
   const int total_kb = (a.k + GEMM_BK - 1) / GEMM_BK;
@@ -1043,9 +1061,12 @@ static int pick_epilogue(const vb_gemm_args& a) {
     return EPI_GENERIC;
   }
   if (a.d_is_f32) return (a.bias == nullptr && a.act == VB_ACT_NONE && a.aux_mode == VB_AUX_NONE) ? EPI_F32 : EPI_GENERIC;
-  if (a.d_preact != nullptr) return (a.act == VB_ACT_GELU && a.aux_mode == VB_AUX_NONE) ? EPI_GELU_PRE : EPI_GENERIC;
-  if (a.aux_mode != VB_AUX_NONE)
-    return (a.bias == nullptr && a.act == VB_ACT_NONE) ? (a.aux_mode == VB_AUX_ADD ? EPI_AUX_ADD : EPI_AUX_GELUGRAD) : EPI_GENERIC;
+  if (a.d_preact != nullptr)
+    return (a.act == VB_ACT_GELU && a.aux_mode == VB_AUX_NONE) ? (a.preact_grad ? EPI_GELU_GRADPRE : EPI_GELU_PRE) : EPI_GENERIC;
+  if (a.aux_mode != VB_AUX_NONE) {
+    if (a.bias != nullptr || a.act != VB_ACT_NONE) return EPI_GENERIC;
+    return a.aux_mode == VB_AUX_ADD ? EPI_AUX_ADD : (a.aux_mode == VB_AUX_MUL ? EPI_AUX_MUL : EPI_AUX_GELUGRAD);
+  }
   return a.act == VB_ACT_NONE ? EPI_BIAS : EPI_GENERIC;
 }
 
@@ -1070,10 +1091,12 @@ static int dispatch_major(const vb_gemm_args& a, int bn, int splits, cudaStream_
         if (epi == EPI_BN_ADD_RELU) return launch_gemm<false, false, CG, NP, OCC, EPI_BN_ADD_RELU>(a, bn, splits, s);
       }
       if (epi == EPI_GELU_PRE) return launch_gemm<false, false, CG, NP, OCC, EPI_GELU_PRE>(a, bn, splits, s);
+      if (epi == EPI_GELU_GRADPRE) return launch_gemm<false, false, CG, NP, OCC, EPI_GELU_GRADPRE>(a, bn, splits, s);
     } else if (!a.a_mn_major && a.b_mn_major) {
       if (epi == EPI_BIAS) return launch_gemm<false, true, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);
       if (epi == EPI_AUX_ADD) return launch_gemm<false, true, CG, NP, OCC, EPI_AUX_ADD>(a, bn, splits, s);
       if (epi == EPI_AUX_GELUGRAD) return launch_gemm<false, true, CG, NP, OCC, EPI_AUX_GELUGRAD>(a, bn, splits, s);
+      if (epi == EPI_AUX_MUL) return launch_gemm<false, true, CG, NP, OCC, EPI_AUX_MUL>(a, bn, splits, s);
     } else if (a.a_mn_major && a.b_mn_major) {
       if (epi == EPI_F32) return launch_gemm<true, true, CG, NP, OCC, EPI_F32>(a, bn, splits, s);
       if (epi == EPI_BIAS) return launch_gemm<true, true, CG, NP, OCC, EPI_BIAS>(a, bn, splits, s);   // bf16 weight gradients (switch exchange)
@@ -1161,6 +1184,8 @@ extern "C" int vb_gemm_bf16(const vb_gemm_args* args, void* stream) {
   VB_REQUIRE(a.splits >= 0 && (a.splits <= 1 || (a.d_is_f32 && a.accumulate)), "split-K needs an fp32 accumulating output");
   VB_REQUIRE(!(a.accumulate && !a.d_is_f32), "accumulate needs an fp32 output");
   VB_REQUIRE(!(a.d_is_f32 && a.d_preact != nullptr), "d_preact only with a bf16 output");
+  VB_REQUIRE(!a.preact_grad || (a.d_preact != nullptr && a.act == VB_ACT_GELU), "preact_grad stores GELU'(pre-activation): needs d_preact and act = GELU");
+  VB_REQUIRE(a.aux_mode >= VB_AUX_NONE && a.aux_mode <= VB_AUX_MUL, "unknown aux_mode");
   VB_REQUIRE(!(a.d_is_f32 && a.aux_mode != VB_AUX_NONE), "aux only with a bf16 output");
   // VB_GEMM_MAX_CTAS: default cap of the persistent grid (data-parallel runs leave a few SMs to the NCCL kernels, so that a
   // GEMM sized for the whole chip does not have to wait for SMs a collective is sitting on)

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_NONE, GemmArgs  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_TANH, AUX_ADD, AUX_MUL, AUX_MUL_GELU_GRAD, AUX_NONE, GemmArgs  # noqa: F401
 
 
 def _stream() -> int:
@@ -31,7 +31,7 @@ def _need_cuda(*ts):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
          bias=None, scale=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, preact=None, accumulate=False,
-         block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False, conv=None) -> torch.Tensor:
+         block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False, conv=None, preact_grad=False) -> torch.Tensor:
     """out[M,N] = epilogue(sum_k A(m,k) B(n,k)).
 
     conv=(kh, kw, stride, pad): `a` is a contiguous NHWC bf16 activation [n, h, w, c] (c % 64 == 0) and the product is the
@@ -73,6 +73,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_mn_major=Fals
     args.lda, args.ldb, args.ldd = (0 if conv is not None else a.stride(0)), b.stride(0), out.stride(0)
     args.conv_n, args.conv_h, args.conv_w, args.conv_c = cn, ch, cw, cc
     args.conv_kh, args.conv_kw, args.conv_stride, args.conv_pad = ckh, ckw, cstride, cpad
+    args.preact_grad = int(preact_grad)      # `preact` receives GELU'(pre-activation) instead of the pre-activation
     args.ld_preact = preact.stride(0) if preact is not None else 0
     args.ld_aux = aux.stride(0) if aux is not None else 0
     args.m, args.n, args.k = m, n, k

@@ -433,6 +433,9 @@ class _Engine:
         # GEMM waiting only for its own block's cast -- 1.5 GB of HBM streaming beside the first layers' compute instead of 0.19 ms
         # in front of them.  VB_REFRESH_IN_GRAPH=0: one cast before the forward (round-2 baseline, A/B runs).
         self.refresh_in_graph = self.refresh_stream is not None and os.environ.get("VB_REFRESH_IN_GRAPH", "1") != "0"
+        # the FFN-1 forward stores GELU'(pre-activation) instead of the pre-activation, so that the FFN-2 dgrad epilogue only
+        # multiplies (it was MUFU-bound: 14.7 us against 11.8 for the same GEMM without it); VB_GELU_GRAD_FWD=0: as before
+        self.gelu_grad_fwd = os.environ.get("VB_GELU_GRAD_FWD", "1") != "0"
         self.refresh_pending = False          # set by _ensure_engine: the next forward carries the refresh
         self._refresh_events: Optional[Dict[str, Any]] = None
         self._refresh_waited = set()
@@ -470,6 +473,10 @@ class _Engine:
                 f.check_contiguous([f"{p}.query{s}.bias", f"{p}.key{s}.bias", f"{p}.value{s}.bias"])
 
     # ------------------------------------------------------------------------------------------------ primitives
+    def _gelu_bwd_mode(self):
+        """What the dgrad of a GELU layer does with the tensor its forward saved: multiply by it (it IS GELU') or by GELU' of it."""
+        return ops.AUX_MUL if self.gelu_grad_fwd else ops.AUX_MUL_GELU_GRAD
+
     def _shadow(self, wkey, rows=None):
         """bf16 shadow of a GEMM weight for a FORWARD kernel on the current stream; during a refreshing forward the stream first
         waits (once per block) for the cast of the block that holds it."""
@@ -518,7 +525,9 @@ class _Engine:
         f = self.flat
         w = self._shadow(wkey, rows)
         bkey = wkey[:-len("weight")] + "bias"
-        ops.gemm(x, w, out, bias=f.m(bkey, w.shape[0]), act=act, preact=preact, b_streamed=True)
+        # GELU layers keep GELU'(pre-activation) for the backward (self.gelu_grad_fwd): the forward epilogue has the tanh anyway
+        ops.gemm(x, w, out, bias=f.m(bkey, w.shape[0]), act=act, preact=preact, b_streamed=True,
+                 preact_grad=self.gelu_grad_fwd and preact is not None and act == ops.ACT_GELU)
 
     def _linear_bwd(self, dy, x, wkey, *, rows=None, dx=None, aux=None, aux_mode=ops.AUX_NONE, bias_grad=True):
         """dW = dy^T x (fp32, straight into the flat gradient buffer), db = colsum(dy) unless already produced by the
@@ -676,7 +685,7 @@ class _Engine:
         g_ares = pl.buf(sc + ".g_ares", (M, H)) if pl.dropout else None
         self._ln_bwd(pl, dy, fo, a, lnkey, sv_ln, dx=g_fo, dres=g_ares, bias_key=pfx_out + ".bias", p_in=p_hidden)
         g_pre = pl.buf(sc + ".g_pre", (M, inter))
-        self._linear_bwd(g_fo, it, pfx_out + ".weight", dx=g_pre, aux=pre, aux_mode=ops.AUX_MUL_GELU_GRAD, bias_grad=False)
+        self._linear_bwd(g_fo, it, pfx_out + ".weight", dx=g_pre, aux=pre, aux_mode=self._gelu_bwd_mode(), bias_grad=False)
         g_a = pl.buf(sc + ".g_a", (M, H))
         self._linear_bwd(g_pre, a, pfx_int + ".weight", dx=g_a, aux=g_ares if g_ares is not None else g_fo, aux_mode=ops.AUX_ADD)
         return g_a

@@ -11,7 +11,7 @@ import torch
 import torch.nn.functional as F
 
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
-AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD = 0, 1, 2
+AUX_NONE, AUX_ADD, AUX_MUL_GELU_GRAD, AUX_MUL = 0, 1, 2, 3
 
 
 IDENTITY_DROPOUT = False     # smoke mode: let the training-mode code paths run with dropout acting as the identity
@@ -22,7 +22,8 @@ def _no_dropout(*ps):
 
 
 def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, scale=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE,
-         preact=None, accumulate=False, block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False, conv=None):
+         preact=None, accumulate=False, block_n=0, splits=0, max_ctas=0, b_streamed=False, d_streamed=False, conv=None,
+         preact_grad=False):
     if conv is not None:                                          # implicit-GEMM convolution: a is the NHWC activation
         kh, kw, stride, pad = conv
         n, h, w, c = a.shape
@@ -37,9 +38,14 @@ def gemm(a, b, out, *, a_mn_major=False, b_mn_major=False, bias=None, scale=None
     if bias is not None:
         v = v + bias
     if preact is not None:
-        preact.copy_(v)
+        if preact_grad:       # GELU'(v) = Phi(v) + v phi(v)
+            preact.copy_(0.5 * (1.0 + torch.erf(v / math.sqrt(2.0))) + v * torch.exp(-0.5 * v * v) / math.sqrt(2.0 * math.pi))
+        else:
+            preact.copy_(v)
     if aux_mode == AUX_ADD:
         v = v + aux.float()
+    elif aux_mode == AUX_MUL:
+        v = v * aux.float()
     elif aux_mode == AUX_MUL_GELU_GRAD:
         x = aux.float()
         v = v * (0.5 * (1.0 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi))

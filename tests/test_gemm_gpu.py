@@ -87,6 +87,19 @@ def test_epilogues():
     torch.nn.functional.gelu(x).sum().backward()
     ops.gemm(a, b, out, aux=aux, aux_mode=ops.AUX_MUL_GELU_GRAD)
     _check(out, base * x.grad)
+    # the forward can store GELU'(pre-activation) itself (one tanh serves the activation and its derivative); the backward GEMM
+    # then only multiplies: both against exact F.gelu and its autograd derivative, for the compiled pair-CTA epilogues and for
+    # the generic one (a single 128-row block runs as a lone CTA)
+    for rows in (m, 96):
+        z = (base[:rows] + bias).detach().requires_grad_(True)
+        torch.nn.functional.gelu(z).sum().backward()
+        gp = torch.empty(rows, n, dtype=torch.bfloat16, device="cuda")
+        o2 = torch.empty(rows, n, dtype=torch.bfloat16, device="cuda")
+        ops.gemm(a[:rows], b, o2, bias=bias, act=ops.ACT_GELU, preact=gp, preact_grad=True)
+        _check(o2, torch.nn.functional.gelu(z.detach()))
+        assert float((gp.float() - z.grad).abs().max()) <= 1e-2            # GELU' is O(1): bf16 storage + the f16x2 tanh
+        ops.gemm(a[:rows], b, o2, aux=gp, aux_mode=ops.AUX_MUL)
+        _check(o2, base[:rows] * gp.float())
 
 
 def test_strided_views():
