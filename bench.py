@@ -193,6 +193,7 @@ def gemm_family_roofline(torch, peaks, wgrad_ctas):
     side streams under that cap, in the shadow of the dgrad chain)."""
     from multimodal_classification_b200 import ops
     bf = torch.bfloat16
+    gelu_grad_fwd = os.environ.get("VB_GELU_GRAD_FWD", "1") != "0"      # as vilbert._Engine
 
     def rnd(*shape):
         return (torch.randn(*shape, device="cuda") * 0.5).to(bf)
@@ -203,10 +204,12 @@ def gemm_family_roofline(torch, peaks, wgrad_ctas):
                                torch.empty(m, k, device="cuda", dtype=bf), rnd(m, k))
         dw = torch.zeros(n, k, device="cuda")
         if gelu:
-            t_f = graph_time(torch, lambda: ops.gemm(x, w, y, bias=bias, act=ops.ACT_GELU, preact=pre, b_streamed=True))
+            t_f = graph_time(torch, lambda: ops.gemm(x, w, y, bias=bias, act=ops.ACT_GELU, preact=pre, b_streamed=True,
+                                                     preact_grad=gelu_grad_fwd))
         else:
             t_f = graph_time(torch, lambda: ops.gemm(x, w, y, bias=bias, b_streamed=True))
-        mode = ops.AUX_MUL_GELU_GRAD if name in ("t.ffn2",) else ops.AUX_ADD     # the dgrad of FFN-2 carries gelu' of FFN-1
+        # the dgrad of FFN-2 carries gelu' of FFN-1: stored by the forward (the engine's default) or recomputed from the pre-activation
+        mode = (ops.AUX_MUL if gelu_grad_fwd else ops.AUX_MUL_GELU_GRAD) if name in ("t.ffn2",) else ops.AUX_ADD
         t_d = graph_time(torch, lambda: ops.gemm(dy, w, dx, b_mn_major=True, aux=aux, aux_mode=mode, b_streamed=True))
         t_w = graph_time(torch, lambda: ops.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, d_streamed=True))
         t_wc = graph_time(torch, lambda: ops.gemm(dy, x, dw, a_mn_major=True, b_mn_major=True, d_streamed=True, max_ctas=wgrad_ctas))

@@ -59,14 +59,14 @@ def bench_gemms():
         dw = torch.zeros(n, k, device="cuda")
         fl = 2.0 * m * n * k
         if gelu:
-            t_f = graph_time(lambda: ops.gemm(x, w, y, bias=bias, act=ops.ACT_GELU, preact=pre))
+            t_f = graph_time(lambda: ops.gemm(x, w, y, bias=bias, act=ops.ACT_GELU, preact=pre, preact_grad=True))      # as the engine
         else:
             t_f = graph_time(lambda: ops.gemm(x, w, y, bias=bias))
         t_fc = graph_time(lambda: torch.matmul(x, w.t(), out=y))
         # dgrad: dx = dy W (+aux)   [for ffn2 the real step fuses gelu' instead]
         if name in ("t.ffn2",):
             auxk = rnd(m, k)
-            t_d = graph_time(lambda: ops.gemm(dy, w, dx, b_mn_major=True, aux=auxk, aux_mode=ops.AUX_MUL_GELU_GRAD))
+            t_d = graph_time(lambda: ops.gemm(dy, w, dx, b_mn_major=True, aux=auxk, aux_mode=ops.AUX_MUL))
         else:
             t_d = graph_time(lambda: ops.gemm(dy, w, dx, b_mn_major=True, aux=aux, aux_mode=ops.AUX_ADD))
         t_dc = graph_time(lambda: torch.matmul(dy, w, out=dx))

@@ -15,9 +15,9 @@ dy768, w_ffn2, g_pre = rnd(m, 768), rnd(768, 3072), torch.empty(m, 3072, device=
 dw = torch.zeros(3072, 768, device="cuda")
 w768, b768, y768 = rnd(768, 768), torch.randn(768, device="cuda"), torch.empty(m, 768, device="cuda", dtype=bf)
 for _ in range(4):
-    ops.gemm(x768, w3072, y, bias=bias, act=ops.ACT_GELU, preact=pre, b_streamed=True)
+    ops.gemm(x768, w3072, y, bias=bias, act=ops.ACT_GELU, preact=pre, b_streamed=True, preact_grad=True)
 for _ in range(4):
-    ops.gemm(dy768, w_ffn2, g_pre, b_mn_major=True, aux=pre, aux_mode=ops.AUX_MUL_GELU_GRAD, b_streamed=True)
+    ops.gemm(dy768, w_ffn2, g_pre, b_mn_major=True, aux=pre, aux_mode=ops.AUX_MUL, b_streamed=True)
 for _ in range(4):
     ops.gemm(y, x768, dw, a_mn_major=True, b_mn_major=True, d_streamed=True)
 for _ in range(4):
