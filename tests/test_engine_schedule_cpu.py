@@ -226,3 +226,63 @@ def test_data_parallel_backward_averages_gradients_over_gloo():
             assert worst_rel <= 0.2, (rank, compress, worst_rel)
     for a, b in zip(res[0], res[1]):                                    # both ranks hold the same averaged gradients
         assert abs(a[3] - b[3]) <= 1e-6 * max(1.0, abs(a[3])), (a, b)
+
+
+def test_shadow_refresh_inside_the_forward_orders_blocks_as_the_forward_touches_them(simulated, monkeypatch):
+    """The bf16 shadow refresh as a branch of the forward (vilbert._Engine._begin_refresh / _shadow): every GEMM weight belongs
+    to exactly one block, blocks are cast in the order the forward first touches them, every stream waits for a block's event
+    before its first GEMM on that block, and after the forward every shadow is the bf16 rounding of its (updated) master."""
+    import ops_sim
+    from multimodal_classification_b200 import ops
+    from multimodal_classification_b200.vilbert import ViLBERTForClassification
+    cfg = vo.tiny_config()
+    sd = vo.seeded_state_dict(cfg)
+    batch = vo.synthetic_batch(cfg, batch=2, seq=16, regions=8, seed=4)
+    model = ViLBERTForClassification(cfg, num_labels=2)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        ref0 = model(**batch)["logits"].clone()
+    eng = model._engine
+    flat = eng.flat
+    assert set(flat.block_of) == set(flat.order_w) and set(flat.block_of.values()) <= set(flat.buckets)
+    order = eng._refresh_order()
+    assert sorted(order) == sorted(flat.buckets) and order[0] == "tail" and order[1] == "t0"
+    # run the refreshing forward over the stand-ins with a recording stream / event pair
+    log = []
+
+    class Ev(ops_sim._Event):
+        def record(self, stream=None):
+            log.append(("cast_done", id(self)))
+
+    class St(ops_sim._Stream):
+        def wait_event(self, event):
+            log.append(("wait", id(event)))
+    main = St()
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: main)
+    casts = []
+    real_cast = ops.cast_bf16
+    monkeypatch.setattr(ops, "cast_bf16", lambda src, dst: (casts.append(src.data_ptr()), real_cast(src, dst))[1])
+    eng.refresh_stream, eng.refresh_in_graph = ops_sim._Stream(), True
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.01)                                   # an optimizer step: versions move
+        out = model(**batch)["logits"]
+    assert not torch.equal(out, ref0)
+    # casts were issued block by block in execution order ...
+    starts = [flat.master[flat.buckets[n][0]:].data_ptr() for n in order if min(flat.buckets[n][1], flat.w_end) > flat.buckets[n][0]]
+    assert [c for c in casts if c in starts] == starts
+    # ... every wait names an event that had been recorded before it (no use before the cast) ...
+    done = set()
+    for kind, ident in log:
+        if kind == "cast_done":
+            done.add(ident)
+        else:
+            assert ident in done
+    assert sum(1 for k, _ in log if k == "wait") >= len(order)
+    # ... and every shadow is fresh
+    for key in flat.order_w:
+        assert torch.equal(flat.w(key), flat.named[key].detach().to(torch.bfloat16)), key
+    ref = vo.forward({k: v.detach() for k, v in model.state_dict().items()}, cfg, **batch)["logits"]
+    assert (out.float() - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
