@@ -728,6 +728,7 @@ class _Engine:
         pl.twins.clear()
         if pl.dropout:
             ops.seed_advance(self.seed, pl.seed)
+        self._refresh_events = None          # (a forward that raised half-way must not leave its events to the next one)
         if self._refresh_now:
             self._begin_refresh(s_t)
         s_v.wait_stream(s_t)
