@@ -150,7 +150,10 @@ def test_shadow_refresh_beside_the_next_copy_follows_every_kind_of_update():
         assert flat._updated is None
         assert torch.equal(flat.w(key), p.detach().to(torch.bfloat16)), step
         ref = vo.forward({k: v.detach().cpu() for k, v in model.state_dict().items()}, cfg, **host)
-        assert abs(out["loss"].item() - ref["loss"].item()) <= 2e-3, step
+        # the fixtures' loss bar (1e-3 at |loss| ~ 0.7), relative to the size the loss has here: the 1.5x edit of a weight matrix
+        # pushes it to ~3.8, and which way the atomically accumulated bias gradients round moves the weights AdamW produces
+        # (measured 1.2e-3 .. 2.5e-3 absolute at step 2 across runs)
+        assert abs(out["loss"].item() - ref["loss"].item()) <= 2e-3 * max(1.0, abs(ref["loss"].item())), step
         out["loss"].backward()
     # a hand-written update through the raw buffer (no version bump): parameters_updated()
     with torch.no_grad():
