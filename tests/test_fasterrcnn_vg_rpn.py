@@ -105,6 +105,17 @@ def test_checkpoint_loader_counts_like_the_reference(tmp_path):
     assert torch.equal(model.RCNN_rpn.RPN_Conv.weight, seeded()[2]["RCNN_rpn.RPN_Conv.weight"])
 
 
+def test_feature_map_size_formula_matches_the_trunk():
+    """The plan sizes its anchor buffers from the picture size alone (FasterRCNNVGRPNExtractor._fmap_hw)."""
+    from multimodal_classification_b200.fasterrcnn_vg_rpn import FasterRCNNVGRPNExtractor as E
+    assert E._fmap_hw(H, W) == (FH, FW)
+    sd = seeded()[0]
+    for h, w in ((97, 131), (160, 224), (33, 250)):
+        with torch.no_grad():
+            fmap = ro.forward_base(sd, torch.zeros(1, 3, h, w))
+        assert E._fmap_hw(h, w) == tuple(fmap.shape[2:]), (h, w)
+
+
 # ------------------------------------------------------------------------------------------------ host schedule on the CPU
 @pytest.fixture
 def simulated(monkeypatch):
